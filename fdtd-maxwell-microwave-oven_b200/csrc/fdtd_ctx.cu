@@ -1,0 +1,1246 @@
+/*
+ * fdtd_ctx.cu -- device context and C ABI of libfdtd_b200.so (declared in include/fdtd_b200.h).
+ *
+ * One context = one z-slab of the cavity resident in the HBM of one B200: the six field arrays
+ * in the pitched layout described in fdtd_kernels.cuh, a compute stream, a halo stream with its
+ * NCCL communicator, and a dump stream with pinned staging.  The host control thread only
+ * queues work; nothing on the stepping path synchronises with the device.
+ */
+#include "fdtd_internal.h"
+#include "fdtd_kernels.cuh"
+
+#include <nccl.h>
+#include <pthread.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+using namespace fdtd;
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            fdtd_set_error("%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return FDTD_E_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+#define NCCL_TRY(expr)                                                                         \
+    do {                                                                                       \
+        ncclResult_t r_ = (expr);                                                              \
+        if (r_ != ncclSuccess) {                                                               \
+            fdtd_set_error("%s: %s (%s:%d)", #expr, ncclGetErrorString(r_), __FILE__, __LINE__); \
+            return FDTD_E_NCCL;                                                                \
+        }                                                                                      \
+    } while (0)
+
+#define FDTD_TRY(expr)                                                                         \
+    do {                                                                                       \
+        int rc_ = (expr);                                                                      \
+        if (rc_ != FDTD_OK)                                                                    \
+            return rc_;                                                                        \
+    } while (0)
+
+namespace {
+
+constexpr int kSrcRing = 512; /* source rows (steps) resident on the device at a time */
+
+struct DumpPipe;
+
+} /* namespace */
+
+struct fdtd_ctx {
+    fdtd_params p;
+    int device, rank, nranks;
+    size_t k0, k1;
+    Geo g;
+    Fld f;
+    double *base;       /* one allocation holding the six arrays */
+    size_t array_elems; /* P * R * planes */
+    double ch, ce;      /* update factors, main.c:441 / :479 */
+
+    cudaStream_t s_main, s_comm, s_dump;
+    cudaEvent_t ev_hb, ev_eb, ev_hhalo, ev_ehalo;
+    bool e_halo_valid, h_halo_valid;
+    ncclComm_t comm;
+    bool has_comm;
+
+    /* source */
+    fdtd_source_plan plan;
+    int src_n;          /* points per row */
+    bool src_here;      /* computation mode and this slab holds k = 0 */
+    double *src_dev;    /* kSrcRing rows of 2*src_n doubles */
+    double *src_host;   /* pinned mirror */
+    cudaEvent_t ev_src; /* last upload of the ring finished */
+    double *src_one_dev; /* single row for the operator-level fdtd_set_source */
+
+    /* options */
+    long opt_kernel, opt_strip, opt_kchunk, opt_wx, opt_wy;
+
+    /* dump scratch for fdtd_aggregate */
+    double *agg_dev;
+    size_t agg_elems;
+
+    /* asynchronous dump pipeline (fdtd_propagate) */
+    DumpPipe *pipe;
+};
+
+namespace {
+
+int check_ctx(const fdtd_ctx *c, const char *who)
+{
+    if (!c) {
+        fdtd_set_error("%s: context is NULL", who);
+        return FDTD_E_ARG;
+    }
+    return FDTD_OK;
+}
+
+int use_device(const fdtd_ctx *c)
+{
+    CUDA_TRY(cudaSetDevice(c->device));
+    return FDTD_OK;
+}
+
+double *field_ptr(const fdtd_ctx *c, int idx)
+{
+    return c->base + (size_t)idx * c->array_elems;
+}
+
+/* dense host shape of each array: row length, rows, planes (main.c:379-407); node = has K+1 planes */
+struct DenseShape {
+    size_t w, h, d;
+    bool node_planes;
+};
+
+DenseShape dense_shape(const fdtd_params &p, int idx)
+{
+    const size_t I = p.maxi, J = p.maxj, K = p.maxk;
+    switch (idx) {
+    case 0: return {I, J + 1, K + 1, true};      /* Ex */
+    case 1: return {I + 1, J, K + 1, true};      /* Ey */
+    case 2: return {I + 1, J + 1, K, false};     /* Ez */
+    case 3: return {I + 1, J, K, false};         /* Hx */
+    case 4: return {I, J + 1, K, false};         /* Hy */
+    default: return {I, J, K + 1, true};         /* Hz */
+    }
+}
+
+/* copy the planes this slab owns between the dense host array and the pitched device array */
+int copy_field(fdtd_ctx *c, int idx, double *host, bool to_device)
+{
+    const DenseShape s = dense_shape(c->p, idx);
+    size_t nplanes = c->g.nk;
+    if (s.node_planes && c->g.top)
+        nplanes += 1;
+    if (nplanes == 0 || s.w == 0 || s.h == 0)
+        return FDTD_OK;
+    double *dev = field_ptr(c, idx) + (size_t)c->g.PR; /* local plane 1 */
+    double *hst = host + c->k0 * s.w * s.h;
+    cudaMemcpy3DParms m;
+    memset(&m, 0, sizeof m);
+    cudaPitchedPtr hp = make_cudaPitchedPtr(hst, s.w * sizeof(double), s.w * sizeof(double), s.h);
+    cudaPitchedPtr dp = make_cudaPitchedPtr(dev, (size_t)c->g.P * sizeof(double),
+                                            (size_t)c->g.P * sizeof(double), (size_t)c->g.R);
+    m.srcPtr = to_device ? hp : dp;
+    m.dstPtr = to_device ? dp : hp;
+    m.extent = make_cudaExtent(s.w * sizeof(double), s.h, nplanes);
+    m.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    CUDA_TRY(cudaMemcpy3DAsync(&m, c->s_main));
+    return FDTD_OK;
+}
+
+Src make_src(const fdtd_ctx *c, const double *row)
+{
+    Src s;
+    s.on = c->src_here ? 1 : 0;
+    s.i0 = (int)c->plan.i0;
+    s.i1 = (int)c->plan.i1;
+    s.j0 = (int)c->plan.j0;
+    s.j1 = (int)c->plan.j1;
+    s.n = c->src_n;
+    s.vals = row;
+    return s;
+}
+
+Src no_src()
+{
+    Src s;
+    memset(&s, 0, sizeof s);
+    return s;
+}
+
+/* ---- launches ------------------------------------------------------------------------------ */
+
+template <int TY>
+void launch_h_march_t(const fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStream_t st)
+{
+    const int wx = (int)c->opt_wx, wy = (int)c->opt_wy;
+    Span sp{kl_begin, kl_end, (int)c->opt_kchunk};
+    dim3 block(32 * wx, wy);
+    dim3 grid((c->g.I + 1 + block.x - 1) / block.x, (c->g.J + 1 + wy * TY - 1) / (wy * TY),
+              (kl_end - kl_begin + sp.kchunk - 1) / sp.kchunk);
+    k_update_h_march<TY><<<grid, block, 0, st>>>(c->g, c->f, c->ch, s, sp);
+}
+
+template <int TY>
+void launch_e_march_t(const fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStream_t st)
+{
+    const int wx = (int)c->opt_wx, wy = (int)c->opt_wy;
+    Span sp{kl_begin, kl_end, (int)c->opt_kchunk};
+    dim3 block(32 * wx, wy);
+    dim3 grid((c->g.I + 1 + block.x - 1) / block.x, (c->g.J + 1 + wy * TY - 1) / (wy * TY),
+              (kl_end - kl_begin + sp.kchunk - 1) / sp.kchunk);
+    k_update_e_march<TY><<<grid, block, 0, st>>>(c->g, c->f, c->ce, s, sp);
+}
+
+/* H update of the local planes [kl_begin, kl_end) */
+void launch_h(const fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStream_t st)
+{
+    if (kl_end <= kl_begin)
+        return;
+    if (c->opt_kernel == 0) {
+        dim3 block(64, 4);
+        dim3 grid((c->g.I + 1 + 63) / 64, (c->g.J + 1 + 3) / 4, kl_end - kl_begin);
+        Geo g = c->g;
+        Fld f = c->f;
+        /* the cell kernel numbers planes from blockIdx.z + 1: shift the base pointers instead */
+        const long long shift = (long long)(kl_begin - 1) * g.PR;
+        f.ex += shift; f.ey += shift; f.ez += shift; f.hx += shift; f.hy += shift; f.hz += shift;
+        g.nk -= (kl_begin - 1);
+        g.kbase += (kl_begin - 1);
+        k_update_h_cell<<<grid, block, 0, st>>>(g, f, c->ch);
+        return;
+    }
+    switch (c->opt_strip) {
+    case 1: launch_h_march_t<1>(c, s, kl_begin, kl_end, st); break;
+    case 2: launch_h_march_t<2>(c, s, kl_begin, kl_end, st); break;
+    default: launch_h_march_t<4>(c, s, kl_begin, kl_end, st); break;
+    }
+}
+
+void launch_e(const fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStream_t st)
+{
+    if (kl_end <= kl_begin)
+        return;
+    if (c->opt_kernel == 0) {
+        dim3 block(64, 4);
+        dim3 grid((c->g.I + 1 + 63) / 64, (c->g.J + 1 + 3) / 4, kl_end - kl_begin);
+        Geo g = c->g;
+        Fld f = c->f;
+        const long long shift = (long long)(kl_begin - 1) * g.PR;
+        f.ex += shift; f.ey += shift; f.ez += shift; f.hx += shift; f.hy += shift; f.hz += shift;
+        g.nk -= (kl_begin - 1);
+        g.kbase += (kl_begin - 1);
+        k_update_e_cell<<<grid, block, 0, st>>>(g, f, c->ce);
+        return;
+    }
+    switch (c->opt_strip) {
+    case 1: launch_e_march_t<1>(c, s, kl_begin, kl_end, st); break;
+    case 2: launch_e_march_t<2>(c, s, kl_begin, kl_end, st); break;
+    default: launch_e_march_t<4>(c, s, kl_begin, kl_end, st); break;
+    }
+}
+
+void launch_set_source(const fdtd_ctx *c, const double *row_dev, cudaStream_t st)
+{
+    const Src s = make_src(c, row_dev);
+    dim3 block(32, 8);
+    dim3 grid((s.i1 - s.i0 + 31) / 32, (s.j1 - s.j0 + 7) / 8);
+    k_set_source<<<grid, block, 0, st>>>(c->g, c->f, s);
+}
+
+/* ---- halo exchange (one plane each way per half-step) ----------------------- */
+
+/* Hx, Hy of my top cell plane go up; the lower neighbour's arrive in my plane 0. */
+int exchange_h(fdtd_ctx *c, cudaStream_t st)
+{
+    if (c->nranks == 1)
+        return FDTD_OK;
+    if (!c->has_comm) {
+        fdtd_set_error("multi-rank context without communicator: call fdtd_ctx_comm_init first");
+        return FDTD_E_STATE;
+    }
+    const size_t n = (size_t)c->g.PR;
+    NCCL_TRY(ncclGroupStart());
+    if (c->rank + 1 < c->nranks) {
+        NCCL_TRY(ncclSend(c->f.hx + n * c->g.nk, n, ncclDouble, c->rank + 1, c->comm, st));
+        NCCL_TRY(ncclSend(c->f.hy + n * c->g.nk, n, ncclDouble, c->rank + 1, c->comm, st));
+    }
+    if (c->rank > 0) {
+        NCCL_TRY(ncclRecv(c->f.hx, n, ncclDouble, c->rank - 1, c->comm, st));
+        NCCL_TRY(ncclRecv(c->f.hy, n, ncclDouble, c->rank - 1, c->comm, st));
+    }
+    NCCL_TRY(ncclGroupEnd());
+    return FDTD_OK;
+}
+
+/* Ex, Ey of my first node plane go down; the upper neighbour's arrive in my plane nk+1.
+ * with_hz: also Hz (only the dump's zone average needs it, main.c:578). */
+int exchange_e(fdtd_ctx *c, cudaStream_t st, bool with_hz)
+{
+    if (c->nranks == 1)
+        return FDTD_OK;
+    if (!c->has_comm) {
+        fdtd_set_error("multi-rank context without communicator: call fdtd_ctx_comm_init first");
+        return FDTD_E_STATE;
+    }
+    const size_t n = (size_t)c->g.PR;
+    NCCL_TRY(ncclGroupStart());
+    if (c->rank > 0) {
+        NCCL_TRY(ncclSend(c->f.ex + n, n, ncclDouble, c->rank - 1, c->comm, st));
+        NCCL_TRY(ncclSend(c->f.ey + n, n, ncclDouble, c->rank - 1, c->comm, st));
+        if (with_hz)
+            NCCL_TRY(ncclSend(c->f.hz + n, n, ncclDouble, c->rank - 1, c->comm, st));
+    }
+    if (c->rank + 1 < c->nranks) {
+        NCCL_TRY(ncclRecv(c->f.ex + n * (c->g.nk + 1), n, ncclDouble, c->rank + 1, c->comm, st));
+        NCCL_TRY(ncclRecv(c->f.ey + n * (c->g.nk + 1), n, ncclDouble, c->rank + 1, c->comm, st));
+        if (with_hz)
+            NCCL_TRY(ncclRecv(c->f.hz + n * (c->g.nk + 1), n, ncclDouble, c->rank + 1, c->comm, st));
+    }
+    NCCL_TRY(ncclGroupEnd());
+    return FDTD_OK;
+}
+
+/* make both halos current on the compute stream (after upload / operator-level calls) */
+int refresh_halos(fdtd_ctx *c)
+{
+    if (c->nranks == 1)
+        return FDTD_OK;
+    if (!c->e_halo_valid) {
+        FDTD_TRY(exchange_e(c, c->s_main, false));
+        c->e_halo_valid = true;
+    }
+    if (!c->h_halo_valid) {
+        FDTD_TRY(exchange_h(c, c->s_main));
+        c->h_halo_valid = true;
+    }
+    return FDTD_OK;
+}
+
+/* One pass of the loop body main.c:770-779 with the halo traffic hidden behind the interior
+ * planes: the boundary plane is updated first, its event releases the halo stream, the
+ * interior follows on the compute stream. */
+int queue_step(fdtd_ctx *c, const Src &s, cudaEvent_t ev_h_begin, cudaEvent_t ev_mid, cudaEvent_t ev_e_end)
+{
+    const int nk = c->g.nk;
+    const int h_end = nk + c->g.top + 1; /* exclusive */
+    if (ev_h_begin)
+        CUDA_TRY(cudaEventRecord(ev_h_begin, c->s_main));
+    if (c->opt_kernel == 0 && c->src_here)
+        launch_set_source(c, s.vals, c->s_main);
+    if (c->nranks == 1) {
+        launch_h(c, s, 1, h_end, c->s_main);
+    } else {
+        CUDA_TRY(cudaStreamWaitEvent(c->s_main, c->ev_ehalo, 0)); /* Ex, Ey of plane nk+1 arrived */
+        const bool sends_up = c->rank + 1 < c->nranks;
+        if (sends_up) {
+            launch_h(c, s, nk, nk + 1, c->s_main); /* boundary plane first */
+            CUDA_TRY(cudaEventRecord(c->ev_hb, c->s_main));
+            launch_h(c, s, 1, nk, c->s_main);
+        } else {
+            launch_h(c, s, 1, h_end, c->s_main);
+            CUDA_TRY(cudaEventRecord(c->ev_hb, c->s_main));
+        }
+        CUDA_TRY(cudaStreamWaitEvent(c->s_comm, c->ev_hb, 0));
+        FDTD_TRY(exchange_h(c, c->s_comm));
+        CUDA_TRY(cudaEventRecord(c->ev_hhalo, c->s_comm));
+    }
+    if (ev_mid)
+        CUDA_TRY(cudaEventRecord(ev_mid, c->s_main));
+    if (c->opt_kernel == 0 && c->src_here)
+        launch_set_source(c, s.vals, c->s_main);
+    if (c->nranks == 1) {
+        launch_e(c, s, 1, nk + 1, c->s_main);
+    } else {
+        CUDA_TRY(cudaStreamWaitEvent(c->s_main, c->ev_hhalo, 0)); /* Hx, Hy of plane 0 arrived */
+        const bool sends_down = c->rank > 0;
+        if (sends_down) {
+            launch_e(c, s, 1, 2, c->s_main);
+            CUDA_TRY(cudaEventRecord(c->ev_eb, c->s_main));
+            launch_e(c, s, 2, nk + 1, c->s_main);
+        } else {
+            launch_e(c, s, 1, nk + 1, c->s_main);
+            CUDA_TRY(cudaEventRecord(c->ev_eb, c->s_main));
+        }
+        CUDA_TRY(cudaStreamWaitEvent(c->s_comm, c->ev_eb, 0));
+        FDTD_TRY(exchange_e(c, c->s_comm, false));
+        CUDA_TRY(cudaEventRecord(c->ev_ehalo, c->s_comm));
+    }
+    if (ev_e_end)
+        CUDA_TRY(cudaEventRecord(ev_e_end, c->s_main));
+    CUDA_TRY(cudaGetLastError());
+    return FDTD_OK;
+}
+
+/* Fill and upload the source rows of steps [0, count) starting at time t (ring slot = step index
+ * modulo kSrcRing).  Returns the time counter after `count` steps through *t_io. */
+int stage_source_rows(fdtd_ctx *c, size_t count, double *t_io)
+{
+    const size_t row = 2 * (size_t)c->src_n;
+    CUDA_TRY(cudaEventSynchronize(c->ev_src)); /* previous upload has left the pinned buffer */
+    double t = *t_io;
+    for (size_t s = 0; s < count; ++s, t += c->p.time_step) {
+        if (c->src_here)
+            FDTD_TRY(fdtd_source_values(&c->p, &c->plan, t, c->src_host + s * row,
+                                        c->src_host + s * row + c->src_n));
+    }
+    if (c->src_here && row > 0) {
+        CUDA_TRY(cudaMemcpyAsync(c->src_dev, c->src_host, count * row * sizeof(double),
+                                 cudaMemcpyHostToDevice, c->s_main));
+        CUDA_TRY(cudaEventRecord(c->ev_src, c->s_main));
+    }
+    *t_io = t;
+    return FDTD_OK;
+}
+
+int run_impl(fdtd_ctx *c, size_t steps, double *time_counter, float *total_ms, float *h_ms, float *e_ms)
+{
+    FDTD_TRY(use_device(c));
+    FDTD_TRY(refresh_halos(c));
+    if (c->nranks > 1) {
+        /* the first step's waits need recorded events */
+        CUDA_TRY(cudaEventRecord(c->ev_ehalo, c->s_main));
+        CUDA_TRY(cudaEventRecord(c->ev_hhalo, c->s_main));
+    }
+    const bool timed = total_ms != nullptr;
+    const bool per_kernel = timed && (h_ms || e_ms);
+    const size_t max_kernel_events = 2048;
+    std::vector<cudaEvent_t> evs;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    if (timed) {
+        CUDA_TRY(cudaEventCreate(&ev_begin));
+        CUDA_TRY(cudaEventCreate(&ev_end));
+        if (per_kernel) {
+            const size_t n = std::min(steps, max_kernel_events);
+            evs.resize(3 * n);
+            for (auto &e : evs)
+                CUDA_TRY(cudaEventCreate(&e));
+        }
+    }
+    double t = *time_counter;
+    const size_t row = 2 * (size_t)c->src_n;
+    bool first = true;
+    for (size_t done = 0; done < steps;) {
+        const size_t chunk = std::min(steps - done, (size_t)kSrcRing);
+        double t_chunk = t;
+        FDTD_TRY(stage_source_rows(c, chunk, &t_chunk));
+        if (first && timed) {
+            CUDA_TRY(cudaStreamSynchronize(c->s_main));
+            CUDA_TRY(cudaEventRecord(ev_begin, c->s_main));
+        }
+        first = false;
+        for (size_t s = 0; s < chunk; ++s) {
+            const Src src = make_src(c, c->src_dev + s * row);
+            const size_t gs = done + s;
+            if (per_kernel && gs * 3 + 2 < evs.size())
+                FDTD_TRY(queue_step(c, src, evs[3 * gs], evs[3 * gs + 1], evs[3 * gs + 2]));
+            else
+                FDTD_TRY(queue_step(c, src, nullptr, nullptr, nullptr));
+        }
+        t = t_chunk;
+        done += chunk;
+    }
+    *time_counter = t;
+    if (timed) {
+        CUDA_TRY(cudaEventRecord(ev_end, c->s_main));
+        if (c->nranks > 1)
+            CUDA_TRY(cudaStreamSynchronize(c->s_comm));
+        CUDA_TRY(cudaStreamSynchronize(c->s_main));
+        CUDA_TRY(cudaEventElapsedTime(total_ms, ev_begin, ev_end));
+        if (per_kernel) {
+            float hs = 0.f, es = 0.f;
+            const size_t n = evs.size() / 3;
+            for (size_t s = 0; s < n; ++s) {
+                float a = 0.f, b = 0.f;
+                CUDA_TRY(cudaEventElapsedTime(&a, evs[3 * s], evs[3 * s + 1]));
+                CUDA_TRY(cudaEventElapsedTime(&b, evs[3 * s + 1], evs[3 * s + 2]));
+                hs += a;
+                es += b;
+            }
+            /* scale to all steps when only the first max_kernel_events were instrumented */
+            const float scale = n ? (float)steps / (float)n : 0.f;
+            if (h_ms) *h_ms = hs * scale;
+            if (e_ms) *e_ms = es * scale;
+            for (auto &e : evs)
+                cudaEventDestroy(e);
+        }
+        cudaEventDestroy(ev_begin);
+        cudaEventDestroy(ev_end);
+    }
+    return FDTD_OK;
+}
+
+int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx **out)
+{
+    if (!p || !out) {
+        fdtd_set_error("fdtd_ctx_create: NULL argument");
+        return FDTD_E_ARG;
+    }
+    if (p->maxi < 1 || p->maxj < 1 || p->maxk < 1 || p->maxi > 60000 || p->maxj > 60000 ||
+        p->maxk > (size_t)1 << 30) {
+        fdtd_set_error("fdtd_ctx_create: unsupported grid %zu x %zu x %zu", p->maxi, p->maxj, p->maxk);
+        return FDTD_E_ARG;
+    }
+    if (p->mode != 0 && p->mode != 1) {
+        fdtd_set_error("fdtd_ctx_create: mode must be 0 (validation) or 1 (computation), got %d", p->mode);
+        return FDTD_E_ARG;
+    }
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) {
+        fdtd_set_error("fdtd_ctx_create: device %d not available (%d visible)", device, ndev);
+        return FDTD_E_CUDA;
+    }
+    fdtd_ctx *c = new (std::nothrow) fdtd_ctx();
+    if (!c) {
+        fdtd_set_error("fdtd_ctx_create: out of host memory");
+        return FDTD_E_NOMEM;
+    }
+    memset(c, 0, sizeof *c);
+    c->p = *p;
+    c->device = device;
+    c->rank = rank;
+    c->nranks = nranks;
+    int rc = fdtd_slab_range(p->maxk, rank, nranks, &c->k0, &c->k1);
+    if (rc != FDTD_OK) {
+        delete c;
+        return rc;
+    }
+    if (c->k1 == c->k0) {
+        fdtd_set_error("fdtd_ctx_create: rank %d of %d owns no plane of a %zu-plane cavity", rank, nranks, p->maxk);
+        delete c;
+        return FDTD_E_ARG;
+    }
+    Geo &g = c->g;
+    g.I = (int)p->maxi;
+    g.J = (int)p->maxj;
+    g.K = (int)p->maxk;
+    g.P = (int)(((p->maxi + 1) + 15) / 16 * 16);
+    g.R = g.J + 1;
+    g.PR = (long long)g.P * g.R;
+    g.nk = (int)(c->k1 - c->k0);
+    g.kbase = (int)c->k0;
+    g.top = (rank == nranks - 1) ? 1 : 0;
+    g.planes = g.nk + 2;
+    c->array_elems = (size_t)g.PR * (size_t)g.planes;
+    c->ch = fdtd_factor_h(p);
+    c->ce = fdtd_factor_e(p);
+    c->opt_kernel = 1;
+    c->opt_strip = 4;
+    c->opt_kchunk = 32;
+    c->opt_wx = 2;
+    c->opt_wy = 4;
+
+    rc = fdtd_source_plan_make(p, &c->plan);
+    if (rc != FDTD_OK) {
+        delete c;
+        return rc;
+    }
+    c->src_n = 0;
+    c->src_here = false;
+    if (p->mode == 1) {
+        /* the reference writes the patch without a bounds check (main.c:745-752); outside the
+         * grid that is undefined behaviour there and an error here */
+        if (c->plan.i0 < 0 || c->plan.j0 < 0 || c->plan.i1 > (long)p->maxi || c->plan.j1 > (long)p->maxj ||
+            c->plan.i1 <= c->plan.i0 || c->plan.j1 <= c->plan.j0) {
+            fdtd_set_error("fdtd_ctx_create: source patch i[%ld,%ld) j[%ld,%ld) does not fit the %zu x %zu grid",
+                           c->plan.i0, c->plan.i1, c->plan.j0, c->plan.j1, p->maxi, p->maxj);
+            delete c;
+            return FDTD_E_ARG;
+        }
+        c->src_n = (int)(c->plan.i1 - c->plan.i0);
+        c->src_here = (c->k0 == 0);
+    }
+
+#define CREATE_TRY(expr)                                                                       \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            fdtd_set_error("%s: %s", #expr, cudaGetErrorString(e_));                           \
+            fdtd_ctx_destroy(c);                                                               \
+            return e_ == cudaErrorMemoryAllocation ? FDTD_E_NOMEM : FDTD_E_CUDA;               \
+        }                                                                                      \
+    } while (0)
+
+    CREATE_TRY(cudaSetDevice(device));
+    CREATE_TRY(cudaMalloc((void **)&c->base, 6 * c->array_elems * sizeof(double)));
+    c->f.ex = field_ptr(c, 0);
+    c->f.ey = field_ptr(c, 1);
+    c->f.ez = field_ptr(c, 2);
+    c->f.hx = field_ptr(c, 3);
+    c->f.hy = field_ptr(c, 4);
+    c->f.hz = field_ptr(c, 5);
+    int lo = 0, hi = 0;
+    CREATE_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CREATE_TRY(cudaStreamCreateWithPriority(&c->s_main, cudaStreamNonBlocking, lo));
+    CREATE_TRY(cudaStreamCreateWithPriority(&c->s_comm, cudaStreamNonBlocking, hi));
+    CREATE_TRY(cudaStreamCreateWithPriority(&c->s_dump, cudaStreamNonBlocking, lo));
+    CREATE_TRY(cudaEventCreateWithFlags(&c->ev_hb, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&c->ev_eb, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&c->ev_hhalo, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&c->ev_ehalo, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&c->ev_src, cudaEventDisableTiming));
+    /* initialize_fields(), main.c:294-364: all zero */
+    CREATE_TRY(cudaMemsetAsync(c->base, 0, 6 * c->array_elems * sizeof(double), c->s_main));
+    const size_t src_row = 2 * (size_t)std::max(c->src_n, 1);
+    CREATE_TRY(cudaMalloc((void **)&c->src_dev, kSrcRing * src_row * sizeof(double)));
+    CREATE_TRY(cudaMalloc((void **)&c->src_one_dev, src_row * sizeof(double)));
+    CREATE_TRY(cudaHostAlloc((void **)&c->src_host, kSrcRing * src_row * sizeof(double), cudaHostAllocDefault));
+    CREATE_TRY(cudaEventRecord(c->ev_src, c->s_main));
+    CREATE_TRY(cudaStreamSynchronize(c->s_main));
+#undef CREATE_TRY
+    c->e_halo_valid = c->h_halo_valid = true; /* all zero: halos agree */
+    *out = c;
+    return FDTD_OK;
+}
+
+void pipe_destroy(fdtd_ctx *c);
+
+} /* namespace */
+
+/* ============================================ C ABI ========================================= */
+
+extern "C" {
+
+int fdtd_ctx_create(const fdtd_params *p, int device, fdtd_ctx **out)
+{
+    return create_impl(p, device, 0, 1, out);
+}
+
+int fdtd_ctx_create_slab(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx **out)
+{
+    if (nranks < 1 || rank < 0 || rank >= nranks) {
+        fdtd_set_error("fdtd_ctx_create_slab: bad rank %d of %d", rank, nranks);
+        return FDTD_E_ARG;
+    }
+    return create_impl(p, device, rank, nranks, out);
+}
+
+int fdtd_ctx_destroy(fdtd_ctx *c)
+{
+    if (!c)
+        return FDTD_OK;
+    cudaSetDevice(c->device);
+    if (c->s_main) cudaStreamSynchronize(c->s_main);
+    if (c->s_comm) cudaStreamSynchronize(c->s_comm);
+    if (c->s_dump) cudaStreamSynchronize(c->s_dump);
+    pipe_destroy(c);
+    if (c->has_comm) ncclCommDestroy(c->comm);
+    if (c->base) cudaFree(c->base);
+    if (c->src_dev) cudaFree(c->src_dev);
+    if (c->src_one_dev) cudaFree(c->src_one_dev);
+    if (c->src_host) cudaFreeHost(c->src_host);
+    if (c->agg_dev) cudaFree(c->agg_dev);
+    cudaEvent_t evs[] = {c->ev_hb, c->ev_eb, c->ev_hhalo, c->ev_ehalo, c->ev_src};
+    for (cudaEvent_t e : evs)
+        if (e) cudaEventDestroy(e);
+    if (c->s_main) cudaStreamDestroy(c->s_main);
+    if (c->s_comm) cudaStreamDestroy(c->s_comm);
+    if (c->s_dump) cudaStreamDestroy(c->s_dump);
+    delete c;
+    return FDTD_OK;
+}
+
+int fdtd_nccl_unique_id(void *id128)
+{
+    if (!id128) {
+        fdtd_set_error("fdtd_nccl_unique_id: NULL argument");
+        return FDTD_E_ARG;
+    }
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NCCL_TRY(ncclGetUniqueId(&id));
+    memcpy(id128, &id, sizeof id);
+    return FDTD_OK;
+}
+
+int fdtd_ctx_comm_init(fdtd_ctx *c, const void *id128)
+{
+    FDTD_TRY(check_ctx(c, "fdtd_ctx_comm_init"));
+    if (!id128) {
+        fdtd_set_error("fdtd_ctx_comm_init: NULL id");
+        return FDTD_E_ARG;
+    }
+    if (c->has_comm) {
+        fdtd_set_error("fdtd_ctx_comm_init: communicator already initialised");
+        return FDTD_E_STATE;
+    }
+    FDTD_TRY(use_device(c));
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    NCCL_TRY(ncclCommInitRank(&c->comm, c->nranks, id, c->rank));
+    c->has_comm = true;
+    return FDTD_OK;
+}
+
+int fdtd_ctx_set_option(fdtd_ctx *c, const char *key, long value)
+{
+    FDTD_TRY(check_ctx(c, "fdtd_ctx_set_option"));
+    if (!key) {
+        fdtd_set_error("fdtd_ctx_set_option: NULL key");
+        return FDTD_E_ARG;
+    }
+    if (!strcmp(key, "kernel") && (value == 0 || value == 1)) c->opt_kernel = value;
+    else if (!strcmp(key, "strip") && (value == 1 || value == 2 || value == 4)) c->opt_strip = value;
+    else if (!strcmp(key, "kchunk") && value >= 1 && value <= 1 << 20) c->opt_kchunk = value;
+    else if (!strcmp(key, "warps_x") && value >= 1 && value <= 8) c->opt_wx = value;
+    else if (!strcmp(key, "warps_y") && value >= 1 && value <= 8) c->opt_wy = value;
+    else {
+        fdtd_set_error("fdtd_ctx_set_option: unknown key or bad value: %s = %ld", key, value);
+        return FDTD_E_ARG;
+    }
+    if (c->opt_wx * c->opt_wy > 8) {
+        fdtd_set_error("fdtd_ctx_set_option: warps_x * warps_y must be <= 8");
+        c->opt_wx = 2;
+        c->opt_wy = 4;
+        return FDTD_E_ARG;
+    }
+    return FDTD_OK;
+}
+
+int fdtd_ctx_get_option(fdtd_ctx *c, const char *key, long *value)
+{
+    FDTD_TRY(check_ctx(c, "fdtd_ctx_get_option"));
+    if (!key || !value) {
+        fdtd_set_error("fdtd_ctx_get_option: NULL argument");
+        return FDTD_E_ARG;
+    }
+    if (!strcmp(key, "kernel")) *value = c->opt_kernel;
+    else if (!strcmp(key, "strip")) *value = c->opt_strip;
+    else if (!strcmp(key, "kchunk")) *value = c->opt_kchunk;
+    else if (!strcmp(key, "warps_x")) *value = c->opt_wx;
+    else if (!strcmp(key, "warps_y")) *value = c->opt_wy;
+    else if (!strcmp(key, "k0")) *value = (long)c->k0;
+    else if (!strcmp(key, "k1")) *value = (long)c->k1;
+    else {
+        fdtd_set_error("fdtd_ctx_get_option: unknown key %s", key);
+        return FDTD_E_ARG;
+    }
+    return FDTD_OK;
+}
+
+int fdtd_ctx_info(fdtd_ctx *c, size_t *hbm_bytes, size_t *pitch, size_t *rows, size_t *planes)
+{
+    FDTD_TRY(check_ctx(c, "fdtd_ctx_info"));
+    if (hbm_bytes) *hbm_bytes = 6 * c->array_elems * sizeof(double) + c->agg_elems * sizeof(double);
+    if (pitch) *pitch = (size_t)c->g.P;
+    if (rows) *rows = (size_t)c->g.R;
+    if (planes) *planes = (size_t)c->g.planes;
+    return FDTD_OK;
+}
+
+int fdtd_upload(fdtd_ctx *c, const fdtd_fields *host)
+{
+    FDTD_TRY(check_ctx(c, "fdtd_upload"));
+    if (!host || !host->Ex || !host->Ey || !host->Ez || !host->Hx || !host->Hy || !host->Hz) {
+        fdtd_set_error("fdtd_upload: NULL field pointer");
+        return FDTD_E_ARG;
+    }
+    FDTD_TRY(use_device(c));
+    double *h[6] = {host->Ex, host->Ey, host->Ez, host->Hx, host->Hy, host->Hz};
+    for (int a = 0; a < 6; ++a)
+        FDTD_TRY(copy_field(c, a, h[a], true));
+    c->e_halo_valid = c->h_halo_valid = (c->nranks == 1);
+    return FDTD_OK;
+}
+
+int fdtd_download(fdtd_ctx *c, const fdtd_fields *host)
+{
+    FDTD_TRY(check_ctx(c, "fdtd_download"));
+    if (!host || !host->Ex || !host->Ey || !host->Ez || !host->Hx || !host->Hy || !host->Hz) {
+        fdtd_set_error("fdtd_download: NULL field pointer");
+        return FDTD_E_ARG;
+    }
+    FDTD_TRY(use_device(c));
+    double *h[6] = {host->Ex, host->Ey, host->Ez, host->Hx, host->Hy, host->Hz};
+    for (int a = 0; a < 6; ++a)
+        FDTD_TRY(copy_field(c, a, h[a], false));
+    CUDA_TRY(cudaStreamSynchronize(c->s_main));
+    return FDTD_OK;
+}
+
+int fdtd_set_initial_conditions(fdtd_ctx *c)
+{
+    FDTD_TRY(check_ctx(c, "fdtd_set_initial_conditions"));
+    FDTD_TRY(use_device(c));
+    /* glibc sin on the host, like the reference (main.c:422-423), then one upload of Ey */
+    const DenseShape s = dense_shape(c->p, 1);
+    double *ey = (double *)malloc(s.w * s.h * s.d * sizeof(double));
+    if (!ey) {
+        fdtd_set_error("fdtd_set_initial_conditions: out of host memory");
+        return FDTD_E_NOMEM;
+    }
+    int rc = fdtd_initial_conditions_host(&c->p, ey);
+    if (rc == FDTD_OK)
+        rc = copy_field(c, 1, ey, true);
+    if (rc == FDTD_OK && cudaStreamSynchronize(c->s_main) != cudaSuccess) {
+        fdtd_set_error("fdtd_set_initial_conditions: upload failed");
+        rc = FDTD_E_CUDA;
+    }
+    free(ey);
+    c->e_halo_valid = (c->nranks == 1);
+    return rc;
+}
+
+int fdtd_set_source(fdtd_ctx *c, double t)
+{
+    FDTD_TRY(check_ctx(c, "fdtd_set_source"));
+    FDTD_TRY(use_device(c));
+    if (c->p.mode != 1 || c->src_n == 0) {
+        fdtd_set_error("fdtd_set_source: context has no source (validation mode)");
+        return FDTD_E_STATE;
+    }
+    if (c->nranks > 1)
+        c->h_halo_valid = false; /* Hx of plane k = 0 may be a plane that travels (same on all ranks) */
+    if (!c->src_here)
+        return FDTD_OK; /* the patch lives on the slab that holds k = 0 */
+    std::vector<double> row(2 * (size_t)c->src_n);
+    FDTD_TRY(fdtd_source_values(&c->p, &c->plan, t, row.data(), row.data() + c->src_n));
+    CUDA_TRY(cudaMemcpyAsync(c->src_one_dev, row.data(), row.size() * sizeof(double),
+                             cudaMemcpyHostToDevice, c->s_main));
+    CUDA_TRY(cudaStreamSynchronize(c->s_main)); /* `row` is pageable and about to go away */
+    launch_set_source(c, c->src_one_dev, c->s_main);
+    CUDA_TRY(cudaGetLastError());
+    return FDTD_OK;
+}
+
+int fdtd_update_H_field(fdtd_ctx *c)
+{
+    FDTD_TRY(check_ctx(c, "fdtd_update_H_field"));
+    FDTD_TRY(use_device(c));
+    FDTD_TRY(refresh_halos(c));
+    launch_h(c, no_src(), 1, c->g.nk + c->g.top + 1, c->s_main);
+    CUDA_TRY(cudaGetLastError());
+    c->h_halo_valid = (c->nranks == 1);
+    return FDTD_OK;
+}
+
+int fdtd_update_E_field(fdtd_ctx *c)
+{
+    FDTD_TRY(check_ctx(c, "fdtd_update_E_field"));
+    FDTD_TRY(use_device(c));
+    FDTD_TRY(refresh_halos(c));
+    launch_e(c, no_src(), 1, c->g.nk + 1, c->s_main);
+    CUDA_TRY(cudaGetLastError());
+    c->e_halo_valid = (c->nranks == 1);
+    return FDTD_OK;
+}
+
+int fdtd_run(fdtd_ctx *c, size_t steps, double *time_counter)
+{
+    FDTD_TRY(check_ctx(c, "fdtd_run"));
+    if (!time_counter) {
+        fdtd_set_error("fdtd_run: time_counter is NULL");
+        return FDTD_E_ARG;
+    }
+    return run_impl(c, steps, time_counter, nullptr, nullptr, nullptr);
+}
+
+int fdtd_run_timed(fdtd_ctx *c, size_t steps, double *time_counter, float *total_ms, float *h_ms, float *e_ms)
+{
+    FDTD_TRY(check_ctx(c, "fdtd_run_timed"));
+    if (!time_counter || !total_ms) {
+        fdtd_set_error("fdtd_run_timed: NULL argument");
+        return FDTD_E_ARG;
+    }
+    return run_impl(c, steps, time_counter, total_ms, h_ms, e_ms);
+}
+
+int fdtd_sync(fdtd_ctx *c)
+{
+    FDTD_TRY(check_ctx(c, "fdtd_sync"));
+    FDTD_TRY(use_device(c));
+    CUDA_TRY(cudaStreamSynchronize(c->s_main));
+    CUDA_TRY(cudaStreamSynchronize(c->s_comm));
+    CUDA_TRY(cudaStreamSynchronize(c->s_dump));
+    return FDTD_OK;
+}
+
+int fdtd_aggregate(fdtd_ctx *c, int var, double *host_out)
+{
+    FDTD_TRY(check_ctx(c, "fdtd_aggregate"));
+    if (var < 0 || var > 5 || !host_out) {
+        fdtd_set_error("fdtd_aggregate: bad argument (var %d)", var);
+        return FDTD_E_ARG;
+    }
+    FDTD_TRY(use_device(c));
+    const size_t n = (size_t)c->g.I * c->g.J * c->g.nk;
+    if (c->agg_elems < n) {
+        if (c->agg_dev) cudaFree(c->agg_dev);
+        c->agg_dev = nullptr;
+        c->agg_elems = 0;
+        CUDA_TRY(cudaMalloc((void **)&c->agg_dev, n * sizeof(double)));
+        c->agg_elems = n;
+    }
+    if (c->nranks > 1) {
+        /* zone plane k1-1 of ex, ey, hz reads node plane k1 (main.c:517-520, 538-539) */
+        c->e_halo_valid = false;
+        FDTD_TRY(exchange_e(c, c->s_main, true));
+        c->e_halo_valid = true;
+    }
+    dim3 block(64, 4);
+    dim3 grid((c->g.I + 63) / 64, (c->g.J + 3) / 4, c->g.nk);
+    k_aggregate<<<grid, block, 0, c->s_main>>>(c->g, field_ptr(c, var), var, c->agg_dev);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(host_out, c->agg_dev, n * sizeof(double), cudaMemcpyDeviceToHost, c->s_main));
+    CUDA_TRY(cudaStreamSynchronize(c->s_main));
+    return FDTD_OK;
+}
+
+} /* extern "C" */
+
+/* ===================================== dumps: fdtd_propagate ================================= */
+
+namespace {
+
+constexpr int kMaxDumpVars = 9;
+const char *const kVarNames[kMaxDumpVars] = {"ex", "ey", "ez", "hx", "hy", "hz", "aEy", "aHx", "aHz"};
+
+/* Writer-side state.  The compute thread aggregates every variable of one dump into HBM scratch
+ * (dev[v]) on the compute stream and posts the iteration number; the writer thread drains the
+ * scratch through two pinned buffers on the dump stream and feeds the sink.  The compute thread
+ * blocks only if the next dump is due before the previous one has left HBM. */
+struct DumpPipe {
+    fdtd_ctx *ctx;
+    fdtd_dump_sink sink;
+    size_t n;                   /* doubles per variable */
+    int nvars;                  /* 6 or 9 */
+    double *dev[7];             /* ex..hz, aEy (aHx/aHz alias hx/hz, main.c:585-588) */
+    double *pinned[2];
+    cudaEvent_t ev_agg, ev_copy[2];
+    double *sk_dev, *si_dev;    /* analytic factors for aEy */
+    double f_mnl;
+
+    pthread_t thread;
+    pthread_mutex_t mu;
+    pthread_cond_t cv;
+    int pending_iteration;      /* -1: none */
+    bool scratch_busy;          /* dev[] still being drained */
+    bool stop;
+    int error;                  /* first sink / CUDA failure seen by the writer */
+    char error_msg[256];
+};
+
+void *writer_main(void *arg)
+{
+    DumpPipe *dp = (DumpPipe *)arg;
+    fdtd_ctx *c = dp->ctx;
+    cudaSetDevice(c->device);
+    for (;;) {
+        pthread_mutex_lock(&dp->mu);
+        while (dp->pending_iteration < 0 && !dp->stop)
+            pthread_cond_wait(&dp->cv, &dp->mu);
+        if (dp->pending_iteration < 0 && dp->stop) {
+            pthread_mutex_unlock(&dp->mu);
+            return nullptr;
+        }
+        const int iteration = dp->pending_iteration;
+        dp->pending_iteration = -1;
+        pthread_mutex_unlock(&dp->mu);
+
+        int err = 0;
+        const char *what = "";
+        const size_t dims[3] = {(size_t)c->g.I, (size_t)c->g.J, (size_t)c->g.nk};
+        if (cudaStreamWaitEvent(c->s_dump, dp->ev_agg, 0) != cudaSuccess) { err = FDTD_E_CUDA; what = "wait for aggregation"; }
+        if (!err && dp->sink.begin && dp->sink.begin(dp->sink.user, iteration, dims, c->k0) != 0) { err = FDTD_E_IO; what = "sink.begin"; }
+        auto source_of = [&](int v) { return v < 7 ? dp->dev[v] : (v == 7 ? dp->dev[3] : dp->dev[5]); };
+        auto start_copy = [&](int v) {
+            if (cudaMemcpyAsync(dp->pinned[v & 1], source_of(v), dp->n * sizeof(double), cudaMemcpyDeviceToHost, c->s_dump) != cudaSuccess ||
+                cudaEventRecord(dp->ev_copy[v & 1], c->s_dump) != cudaSuccess) {
+                err = FDTD_E_CUDA;
+                what = "device-to-host copy";
+            }
+        };
+        if (!err)
+            start_copy(0);
+        for (int v = 0; v < dp->nvars && !err; ++v) {
+            if (cudaEventSynchronize(dp->ev_copy[v & 1]) != cudaSuccess) { err = FDTD_E_CUDA; what = "device-to-host copy"; break; }
+            if (v + 1 < dp->nvars)
+                start_copy(v + 1); /* overlaps with the sink consuming variable v */
+            else {
+                /* the last variable has left HBM: the compute thread may aggregate the next dump */
+                pthread_mutex_lock(&dp->mu);
+                dp->scratch_busy = false;
+                pthread_cond_broadcast(&dp->cv);
+                pthread_mutex_unlock(&dp->mu);
+            }
+            if (!err && dp->sink.variable &&
+                dp->sink.variable(dp->sink.user, kVarNames[v], dp->pinned[v & 1], dp->n) != 0) { err = FDTD_E_IO; what = "sink.variable"; }
+        }
+        if (!err && dp->sink.end && dp->sink.end(dp->sink.user) != 0) { err = FDTD_E_IO; what = "sink.end"; }
+        pthread_mutex_lock(&dp->mu);
+        if (err && !dp->error) {
+            dp->error = err;
+            snprintf(dp->error_msg, sizeof dp->error_msg, "dump of iteration %d failed in %s", iteration, what);
+        }
+        dp->scratch_busy = false;
+        pthread_cond_broadcast(&dp->cv);
+        pthread_mutex_unlock(&dp->mu);
+    }
+}
+
+int pipe_create(fdtd_ctx *c, const fdtd_dump_sink *sink)
+{
+    DumpPipe *dp = new (std::nothrow) DumpPipe();
+    if (!dp) {
+        fdtd_set_error("fdtd_propagate: out of host memory");
+        return FDTD_E_NOMEM;
+    }
+    memset(dp, 0, sizeof *dp);
+    c->pipe = dp;
+    dp->ctx = c;
+    dp->sink = *sink;
+    dp->n = (size_t)c->g.I * c->g.J * c->g.nk;
+    dp->nvars = c->p.mode == 0 ? 9 : 6;
+    dp->pending_iteration = -1;
+    const int ndev = c->p.mode == 0 ? 7 : 6;
+    for (int v = 0; v < ndev; ++v)
+        CUDA_TRY(cudaMalloc((void **)&dp->dev[v], dp->n * sizeof(double)));
+    for (int b = 0; b < 2; ++b) {
+        CUDA_TRY(cudaHostAlloc((void **)&dp->pinned[b], dp->n * sizeof(double), cudaHostAllocDefault));
+        CUDA_TRY(cudaEventCreateWithFlags(&dp->ev_copy[b], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&dp->ev_agg, cudaEventDisableTiming));
+    if (c->p.mode == 0) {
+        /* factors of the analytic TE101 solution, main.c:672 and :688-690, with the host libm */
+        const fdtd_params &p = c->p;
+        std::vector<double> sk(p.maxk + 2), si(p.maxi + 2);
+        for (size_t k = 0; k < p.maxk + 1; ++k)
+            sk[k] = sin(FDTD_PI * k * p.spatial_step / p.height);
+        for (size_t i = 0; i < p.maxi + 1; ++i)
+            si[i] = sin(FDTD_PI * i * p.spatial_step / p.length);
+        dp->f_mnl = 0.5 * FDTD_CELERITY * sqrt(pow(FDTD_PI / p.height, 2) + pow(FDTD_PI / p.length, 2)) / FDTD_PI;
+        CUDA_TRY(cudaMalloc((void **)&dp->sk_dev, sk.size() * sizeof(double)));
+        CUDA_TRY(cudaMalloc((void **)&dp->si_dev, si.size() * sizeof(double)));
+        CUDA_TRY(cudaMemcpy(dp->sk_dev, sk.data(), sk.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(dp->si_dev, si.data(), si.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    pthread_mutex_init(&dp->mu, nullptr);
+    pthread_cond_init(&dp->cv, nullptr);
+    if (pthread_create(&dp->thread, nullptr, writer_main, dp) != 0) {
+        fdtd_set_error("fdtd_propagate: cannot start the writer thread");
+        return FDTD_E_STATE;
+    }
+    return FDTD_OK;
+}
+
+void pipe_destroy(fdtd_ctx *c)
+{
+    DumpPipe *dp = c->pipe;
+    if (!dp)
+        return;
+    if (dp->thread) {
+        pthread_mutex_lock(&dp->mu);
+        dp->stop = true;
+        pthread_cond_broadcast(&dp->cv);
+        pthread_mutex_unlock(&dp->mu);
+        pthread_join(dp->thread, nullptr);
+        pthread_mutex_destroy(&dp->mu);
+        pthread_cond_destroy(&dp->cv);
+    }
+    for (int v = 0; v < 7; ++v)
+        if (dp->dev[v]) cudaFree(dp->dev[v]);
+    for (int b = 0; b < 2; ++b) {
+        if (dp->pinned[b]) cudaFreeHost(dp->pinned[b]);
+        if (dp->ev_copy[b]) cudaEventDestroy(dp->ev_copy[b]);
+    }
+    if (dp->ev_agg) cudaEventDestroy(dp->ev_agg);
+    if (dp->sk_dev) cudaFree(dp->sk_dev);
+    if (dp->si_dev) cudaFree(dp->si_dev);
+    delete dp;
+    c->pipe = nullptr;
+}
+
+/* write_silo(), main.c:550-598, device side: aggregate every variable of the current state.
+ * t_validation is the time the validation fields were last evaluated for (main.c:762, :783). */
+int post_dump(fdtd_ctx *c, int iteration, double t_validation)
+{
+    DumpPipe *dp = c->pipe;
+    pthread_mutex_lock(&dp->mu);
+    while (dp->scratch_busy && !dp->error)
+        pthread_cond_wait(&dp->cv, &dp->mu);
+    const int err = dp->error;
+    if (!err)
+        dp->scratch_busy = true;
+    pthread_mutex_unlock(&dp->mu);
+    if (err) {
+        fdtd_set_error("%s", dp->error_msg);
+        return err;
+    }
+    if (c->nranks > 1) {
+        c->e_halo_valid = false;
+        FDTD_TRY(exchange_e(c, c->s_main, true)); /* node plane k1 of Ex, Ey, Hz for the top zone plane */
+        c->e_halo_valid = true;
+    }
+    dim3 block(64, 4);
+    dim3 grid((c->g.I + 63) / 64, (c->g.J + 3) / 4, c->g.nk);
+    for (int v = 0; v < 6; ++v)
+        k_aggregate<<<grid, block, 0, c->s_main>>>(c->g, field_ptr(c, v), v, dp->dev[v]);
+    if (c->p.mode == 0) {
+        const double ct = cos(2 * FDTD_PI * dp->f_mnl * t_validation); /* main.c:688 */
+        k_aggregate_aey<<<grid, block, 0, c->s_main>>>(c->g, c->f.ey, ct, dp->sk_dev, dp->si_dev, dp->dev[6]);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(dp->ev_agg, c->s_main));
+    pthread_mutex_lock(&dp->mu);
+    dp->pending_iteration = iteration;
+    pthread_cond_broadcast(&dp->cv);
+    pthread_mutex_unlock(&dp->mu);
+    return FDTD_OK;
+}
+
+} /* namespace */
+
+extern "C" {
+
+int fdtd_propagate(fdtd_ctx *c, const fdtd_dump_sink *sink, size_t *steps_done, double *time_counter)
+{
+    FDTD_TRY(check_ctx(c, "fdtd_propagate"));
+    FDTD_TRY(use_device(c));
+    if (sink && c->p.sampling_rate == 0) {
+        /* the reference divides by zero at main.c:794 */
+        fdtd_set_error("fdtd_propagate: sampling_rate must be >= 1");
+        return FDTD_E_ARG;
+    }
+    if (sink) {
+        pipe_destroy(c);
+        int rc = pipe_create(c, sink);
+        if (rc != FDTD_OK) {
+            pipe_destroy(c);
+            return rc;
+        }
+    }
+    int rc = FDTD_OK;
+    int iteration = 1; /* main.c:758 */
+    size_t steps = 0;
+    double t = 0.0;
+    if (sink)
+        rc = post_dump(c, iteration, 0.0); /* main.c:762-764 */
+    /* main.c:765: double counter, repeated addition, float bound promoted to double, `<=` */
+    while (rc == FDTD_OK && t <= c->p.simulation_time) {
+        /* queue every step up to the next dump in one go */
+        size_t batch = 0;
+        double t_probe = t, t_last = t;
+        int it_probe = iteration;
+        while (t_probe <= c->p.simulation_time) {
+            ++batch;
+            t_last = t_probe;
+            t_probe += c->p.time_step;
+            if (sink && it_probe % (int)c->p.sampling_rate == 0)
+                break;
+            ++it_probe;
+            if (!sink && batch >= 4096)
+                break;
+        }
+        rc = run_impl(c, batch, &t, nullptr, nullptr, nullptr);
+        if (rc != FDTD_OK)
+            break;
+        steps += batch;
+        iteration += (int)batch;
+        /* main.c:794: the test runs before `iteration++`, i.e. on the index of the pass just done */
+        if (sink && (iteration - 1) % (int)c->p.sampling_rate == 0)
+            rc = post_dump(c, iteration - 1, t_last);
+    }
+    if (rc == FDTD_OK)
+        rc = fdtd_sync(c);
+    if (c->pipe) {
+        DumpPipe *dp = c->pipe;
+        pthread_mutex_lock(&dp->mu);
+        while ((dp->scratch_busy || dp->pending_iteration >= 0) && !dp->error)
+            pthread_cond_wait(&dp->cv, &dp->mu);
+        if (dp->error && rc == FDTD_OK) {
+            rc = dp->error;
+            fdtd_set_error("%s", dp->error_msg);
+        }
+        pthread_mutex_unlock(&dp->mu);
+        pipe_destroy(c); /* joins the writer after its last sink.end() */
+    }
+    if (steps_done) *steps_done = steps;
+    if (time_counter) *time_counter = t;
+    return rc;
+}
+
+static DenseView dense_view(const fdtd_ctx *c, int idx)
+{
+    const DenseShape s = dense_shape(c->p, idx);
+    DenseView v;
+    v.w = (int)s.w;
+    v.h = (int)s.h;
+    v.np = c->g.nk + ((s.node_planes && c->g.top) ? 1 : 0);
+    v.kd0 = (long long)c->k0;
+    return v;
+}
+
+int fdtd_fill_test_pattern(fdtd_ctx *c, unsigned long long seed)
+{
+    FDTD_TRY(check_ctx(c, "fdtd_fill_test_pattern"));
+    FDTD_TRY(use_device(c));
+    CUDA_TRY(cudaMemsetAsync(c->base, 0, 6 * c->array_elems * sizeof(double), c->s_main));
+    for (int a = 0; a < 6; ++a) {
+        const DenseView v = dense_view(c, a);
+        dim3 block(64, 4);
+        dim3 grid((v.w + 63) / 64, (v.h + 3) / 4, v.np);
+        k_fill_pattern<<<grid, block, 0, c->s_main>>>(c->g, field_ptr(c, a), v, seed, a);
+    }
+    CUDA_TRY(cudaGetLastError());
+    c->e_halo_valid = c->h_halo_valid = (c->nranks == 1);
+    return FDTD_OK;
+}
+
+int fdtd_checksum(fdtd_ctx *c, unsigned long long out[6])
+{
+    FDTD_TRY(check_ctx(c, "fdtd_checksum"));
+    if (!out) {
+        fdtd_set_error("fdtd_checksum: NULL argument");
+        return FDTD_E_ARG;
+    }
+    FDTD_TRY(use_device(c));
+    unsigned long long *dev = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&dev, 6 * sizeof(unsigned long long)));
+    cudaMemsetAsync(dev, 0, 6 * sizeof(unsigned long long), c->s_main);
+    for (int a = 0; a < 6; ++a) {
+        const DenseView v = dense_view(c, a);
+        dim3 block(64, 4);
+        dim3 grid((v.w + 63) / 64, (v.h + 3) / 4, v.np);
+        k_checksum<<<grid, block, 0, c->s_main>>>(c->g, field_ptr(c, a), v, dev + a);
+    }
+    cudaError_t e = cudaMemcpyAsync(out, dev, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->s_main);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(c->s_main);
+    cudaFree(dev);
+    if (e != cudaSuccess) {
+        fdtd_set_error("fdtd_checksum: %s", cudaGetErrorString(e));
+        return FDTD_E_CUDA;
+    }
+    return FDTD_OK;
+}
+
+int fdtd_host_alloc(size_t bytes, void **out)
+{
+    if (!out) {
+        fdtd_set_error("fdtd_host_alloc: NULL argument");
+        return FDTD_E_ARG;
+    }
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        fdtd_set_error("cudaHostAlloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+        *out = nullptr;
+        return e == cudaErrorMemoryAllocation ? FDTD_E_NOMEM : FDTD_E_CUDA;
+    }
+    return FDTD_OK;
+}
+
+int fdtd_host_free(void *ptr)
+{
+    if (ptr)
+        CUDA_TRY(cudaFreeHost(ptr));
+    return FDTD_OK;
+}
+
+} /* extern "C" */
