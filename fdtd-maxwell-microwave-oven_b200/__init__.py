@@ -86,6 +86,8 @@ SIGNATURES = {
     "fdtd_ctx_get_option": (C.c_int, [_CTX, C.c_char_p, C.POINTER(C.c_long)]),
     "fdtd_upload": (C.c_int, [_CTX, C.POINTER(FieldPtrs)]),
     "fdtd_download": (C.c_int, [_CTX, C.POINTER(FieldPtrs)]),
+    "fdtd_upload_slab": (C.c_int, [_CTX, C.POINTER(FieldPtrs)]),
+    "fdtd_download_slab": (C.c_int, [_CTX, C.POINTER(FieldPtrs)]),
     "fdtd_set_initial_conditions": (C.c_int, [_CTX]),
     "fdtd_set_source": (C.c_int, [_CTX, C.c_double]),
     "fdtd_update_H_field": (C.c_int, [_CTX]),
@@ -183,10 +185,10 @@ def nccl_unique_id() -> bytes:
 class PinnedArrays:
     """Six pinned host arrays in the reference's dense layout (fdtd_host_alloc)."""
 
-    def __init__(self, p, fill=None):
+    def __init__(self, p, fill=None, shapes=None):
         self._ptrs = []
         self.arrays = {}
-        for name, shape in field_shapes(p).items():
+        for name, shape in (shapes or field_shapes(p)).items():
             n = int(np.prod(shape))
             ptr = C.c_void_p()
             _check(lib.fdtd_host_alloc(max(n, 1) * 8, C.byref(ptr)))
@@ -268,6 +270,22 @@ class Context:
         if out is None:
             out = {n: np.zeros(s) for n, s in field_shapes(self.p).items()}
         _check(lib.fdtd_download(self._h, C.byref(_ptrs(out))))
+        return out
+
+    def slab_shapes(self):
+        """dense shapes of the arrays holding only this slab's planes (fdtd_upload_slab)."""
+        nk = self.k1 - self.k0
+        top = 1 if self.rank == self.nranks - 1 else 0
+        out = {}
+        for name, (planes, rows, cols) in field_shapes(self.p).items():
+            out[name] = ((nk + top) if name in ("Ex", "Ey", "Hz") else nk, rows, cols)
+        return out
+
+    def upload_slab(self, fields):
+        _check(lib.fdtd_upload_slab(self._h, C.byref(_ptrs(fields))))
+
+    def download_slab(self, out):
+        _check(lib.fdtd_download_slab(self._h, C.byref(_ptrs(out))))
         return out
 
     def set_initial_conditions(self):

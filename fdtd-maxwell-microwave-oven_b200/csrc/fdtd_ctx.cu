@@ -9,6 +9,7 @@
 #include "fdtd_internal.h"
 #include "fdtd_kernels.cuh"
 
+#include <dlfcn.h>
 #include <nccl.h>
 #include <pthread.h>
 
@@ -33,7 +34,7 @@ using namespace fdtd;
     do {                                                                                       \
         ncclResult_t r_ = (expr);                                                              \
         if (r_ != ncclSuccess) {                                                               \
-            fdtd_set_error("%s: %s (%s:%d)", #expr, ncclGetErrorString(r_), __FILE__, __LINE__); \
+            fdtd_set_error("%s: %s (%s:%d)", #expr, g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
             return FDTD_E_NCCL;                                                                \
         }                                                                                      \
     } while (0)
@@ -46,6 +47,54 @@ using namespace fdtd;
     } while (0)
 
 namespace {
+
+/* NCCL is bound at run time, on first multi-GPU use, instead of at link time: a process that has
+ * already loaded a libnccl.so.2 (e.g. the one PyTorch ships) keeps using that very library, and a
+ * single-GPU run never loads NCCL at all. */
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)(void);
+    ncclResult_t (*GroupEnd)(void);
+    const char *(*GetErrorString)(ncclResult_t);
+    bool ok;
+} g_nccl;
+
+int nccl_bind()
+{
+    static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+    pthread_mutex_lock(&mu);
+    if (!g_nccl.ok) {
+        const char *name = getenv("FDTD_B200_NCCL_LIB");
+        void *h = name ? dlopen(name, RTLD_NOW | RTLD_GLOBAL) : dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!h && !name)
+            h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (h) {
+#define BIND(field, sym) *(void **)(&g_nccl.field) = dlsym(h, sym)
+            BIND(GetUniqueId, "ncclGetUniqueId");
+            BIND(CommInitRank, "ncclCommInitRank");
+            BIND(CommDestroy, "ncclCommDestroy");
+            BIND(Send, "ncclSend");
+            BIND(Recv, "ncclRecv");
+            BIND(GroupStart, "ncclGroupStart");
+            BIND(GroupEnd, "ncclGroupEnd");
+            BIND(GetErrorString, "ncclGetErrorString");
+#undef BIND
+            g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.Send &&
+                        g_nccl.Recv && g_nccl.GroupStart && g_nccl.GroupEnd && g_nccl.GetErrorString;
+        }
+    }
+    const bool ok = g_nccl.ok;
+    pthread_mutex_unlock(&mu);
+    if (!ok) {
+        fdtd_set_error("cannot load NCCL (libnccl.so.2): %s", dlerror() ? dlerror() : "symbols missing");
+        return FDTD_E_NCCL;
+    }
+    return FDTD_OK;
+}
 
 constexpr int kSrcRing = 512; /* source rows (steps) resident on the device at a time */
 
@@ -80,6 +129,7 @@ struct fdtd_ctx {
 
     /* options */
     long opt_kernel, opt_strip, opt_kchunk, opt_wx, opt_wy;
+    mutable long launches; /* kernels of this library launched so far (reports) */
 
     /* dump scratch for fdtd_aggregate */
     double *agg_dev;
@@ -131,7 +181,7 @@ DenseShape dense_shape(const fdtd_params &p, int idx)
 }
 
 /* copy the planes this slab owns between the dense host array and the pitched device array */
-int copy_field(fdtd_ctx *c, int idx, double *host, bool to_device)
+int copy_field(fdtd_ctx *c, int idx, double *host_first_owned_plane, bool to_device)
 {
     const DenseShape s = dense_shape(c->p, idx);
     size_t nplanes = c->g.nk;
@@ -140,7 +190,7 @@ int copy_field(fdtd_ctx *c, int idx, double *host, bool to_device)
     if (nplanes == 0 || s.w == 0 || s.h == 0)
         return FDTD_OK;
     double *dev = field_ptr(c, idx) + (size_t)c->g.PR; /* local plane 1 */
-    double *hst = host + c->k0 * s.w * s.h;
+    double *hst = host_first_owned_plane;
     cudaMemcpy3DParms m;
     memset(&m, 0, sizeof m);
     cudaPitchedPtr hp = make_cudaPitchedPtr(hst, s.w * sizeof(double), s.w * sizeof(double), s.h);
@@ -185,6 +235,7 @@ void launch_h_march_t(const fdtd_ctx *c, const Src &s, int kl_begin, int kl_end,
     dim3 grid((c->g.I + 1 + block.x - 1) / block.x, (c->g.J + 1 + wy * TY - 1) / (wy * TY),
               (kl_end - kl_begin + sp.kchunk - 1) / sp.kchunk);
     k_update_h_march<TY><<<grid, block, 0, st>>>(c->g, c->f, c->ch, s, sp);
+    ++c->launches;
 }
 
 template <int TY>
@@ -196,6 +247,7 @@ void launch_e_march_t(const fdtd_ctx *c, const Src &s, int kl_begin, int kl_end,
     dim3 grid((c->g.I + 1 + block.x - 1) / block.x, (c->g.J + 1 + wy * TY - 1) / (wy * TY),
               (kl_end - kl_begin + sp.kchunk - 1) / sp.kchunk);
     k_update_e_march<TY><<<grid, block, 0, st>>>(c->g, c->f, c->ce, s, sp);
+    ++c->launches;
 }
 
 /* H update of the local planes [kl_begin, kl_end) */
@@ -214,6 +266,7 @@ void launch_h(const fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStr
         g.nk -= (kl_begin - 1);
         g.kbase += (kl_begin - 1);
         k_update_h_cell<<<grid, block, 0, st>>>(g, f, c->ch);
+        ++c->launches;
         return;
     }
     switch (c->opt_strip) {
@@ -237,6 +290,7 @@ void launch_e(const fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStr
         g.nk -= (kl_begin - 1);
         g.kbase += (kl_begin - 1);
         k_update_e_cell<<<grid, block, 0, st>>>(g, f, c->ce);
+        ++c->launches;
         return;
     }
     switch (c->opt_strip) {
@@ -252,6 +306,7 @@ void launch_set_source(const fdtd_ctx *c, const double *row_dev, cudaStream_t st
     dim3 block(32, 8);
     dim3 grid((s.i1 - s.i0 + 31) / 32, (s.j1 - s.j0 + 7) / 8);
     k_set_source<<<grid, block, 0, st>>>(c->g, c->f, s);
+    ++c->launches;
 }
 
 /* ---- halo exchange (one plane each way per half-step) ----------------------- */
@@ -266,16 +321,16 @@ int exchange_h(fdtd_ctx *c, cudaStream_t st)
         return FDTD_E_STATE;
     }
     const size_t n = (size_t)c->g.PR;
-    NCCL_TRY(ncclGroupStart());
+    NCCL_TRY(g_nccl.GroupStart());
     if (c->rank + 1 < c->nranks) {
-        NCCL_TRY(ncclSend(c->f.hx + n * c->g.nk, n, ncclDouble, c->rank + 1, c->comm, st));
-        NCCL_TRY(ncclSend(c->f.hy + n * c->g.nk, n, ncclDouble, c->rank + 1, c->comm, st));
+        NCCL_TRY(g_nccl.Send(c->f.hx + n * c->g.nk, n, ncclDouble, c->rank + 1, c->comm, st));
+        NCCL_TRY(g_nccl.Send(c->f.hy + n * c->g.nk, n, ncclDouble, c->rank + 1, c->comm, st));
     }
     if (c->rank > 0) {
-        NCCL_TRY(ncclRecv(c->f.hx, n, ncclDouble, c->rank - 1, c->comm, st));
-        NCCL_TRY(ncclRecv(c->f.hy, n, ncclDouble, c->rank - 1, c->comm, st));
+        NCCL_TRY(g_nccl.Recv(c->f.hx, n, ncclDouble, c->rank - 1, c->comm, st));
+        NCCL_TRY(g_nccl.Recv(c->f.hy, n, ncclDouble, c->rank - 1, c->comm, st));
     }
-    NCCL_TRY(ncclGroupEnd());
+    NCCL_TRY(g_nccl.GroupEnd());
     return FDTD_OK;
 }
 
@@ -290,20 +345,20 @@ int exchange_e(fdtd_ctx *c, cudaStream_t st, bool with_hz)
         return FDTD_E_STATE;
     }
     const size_t n = (size_t)c->g.PR;
-    NCCL_TRY(ncclGroupStart());
+    NCCL_TRY(g_nccl.GroupStart());
     if (c->rank > 0) {
-        NCCL_TRY(ncclSend(c->f.ex + n, n, ncclDouble, c->rank - 1, c->comm, st));
-        NCCL_TRY(ncclSend(c->f.ey + n, n, ncclDouble, c->rank - 1, c->comm, st));
+        NCCL_TRY(g_nccl.Send(c->f.ex + n, n, ncclDouble, c->rank - 1, c->comm, st));
+        NCCL_TRY(g_nccl.Send(c->f.ey + n, n, ncclDouble, c->rank - 1, c->comm, st));
         if (with_hz)
-            NCCL_TRY(ncclSend(c->f.hz + n, n, ncclDouble, c->rank - 1, c->comm, st));
+            NCCL_TRY(g_nccl.Send(c->f.hz + n, n, ncclDouble, c->rank - 1, c->comm, st));
     }
     if (c->rank + 1 < c->nranks) {
-        NCCL_TRY(ncclRecv(c->f.ex + n * (c->g.nk + 1), n, ncclDouble, c->rank + 1, c->comm, st));
-        NCCL_TRY(ncclRecv(c->f.ey + n * (c->g.nk + 1), n, ncclDouble, c->rank + 1, c->comm, st));
+        NCCL_TRY(g_nccl.Recv(c->f.ex + n * (c->g.nk + 1), n, ncclDouble, c->rank + 1, c->comm, st));
+        NCCL_TRY(g_nccl.Recv(c->f.ey + n * (c->g.nk + 1), n, ncclDouble, c->rank + 1, c->comm, st));
         if (with_hz)
-            NCCL_TRY(ncclRecv(c->f.hz + n * (c->g.nk + 1), n, ncclDouble, c->rank + 1, c->comm, st));
+            NCCL_TRY(g_nccl.Recv(c->f.hz + n * (c->g.nk + 1), n, ncclDouble, c->rank + 1, c->comm, st));
     }
-    NCCL_TRY(ncclGroupEnd());
+    NCCL_TRY(g_nccl.GroupEnd());
     return FDTD_OK;
 }
 
@@ -631,7 +686,7 @@ int fdtd_ctx_destroy(fdtd_ctx *c)
     if (c->s_comm) cudaStreamSynchronize(c->s_comm);
     if (c->s_dump) cudaStreamSynchronize(c->s_dump);
     pipe_destroy(c);
-    if (c->has_comm) ncclCommDestroy(c->comm);
+    if (c->has_comm) g_nccl.CommDestroy(c->comm);
     if (c->base) cudaFree(c->base);
     if (c->src_dev) cudaFree(c->src_dev);
     if (c->src_one_dev) cudaFree(c->src_one_dev);
@@ -654,8 +709,9 @@ int fdtd_nccl_unique_id(void *id128)
         return FDTD_E_ARG;
     }
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    FDTD_TRY(nccl_bind());
     ncclUniqueId id;
-    NCCL_TRY(ncclGetUniqueId(&id));
+    NCCL_TRY(g_nccl.GetUniqueId(&id));
     memcpy(id128, &id, sizeof id);
     return FDTD_OK;
 }
@@ -672,9 +728,10 @@ int fdtd_ctx_comm_init(fdtd_ctx *c, const void *id128)
         return FDTD_E_STATE;
     }
     FDTD_TRY(use_device(c));
+    FDTD_TRY(nccl_bind());
     ncclUniqueId id;
     memcpy(&id, id128, sizeof id);
-    NCCL_TRY(ncclCommInitRank(&c->comm, c->nranks, id, c->rank));
+    NCCL_TRY(g_nccl.CommInitRank(&c->comm, c->nranks, id, c->rank));
     c->has_comm = true;
     return FDTD_OK;
 }
@@ -718,6 +775,7 @@ int fdtd_ctx_get_option(fdtd_ctx *c, const char *key, long *value)
     else if (!strcmp(key, "warps_y")) *value = c->opt_wy;
     else if (!strcmp(key, "k0")) *value = (long)c->k0;
     else if (!strcmp(key, "k1")) *value = (long)c->k1;
+    else if (!strcmp(key, "launches")) *value = c->launches;
     else {
         fdtd_set_error("fdtd_ctx_get_option: unknown key %s", key);
         return FDTD_E_ARG;
@@ -735,7 +793,21 @@ int fdtd_ctx_info(fdtd_ctx *c, size_t *hbm_bytes, size_t *pitch, size_t *rows, s
     return FDTD_OK;
 }
 
-int fdtd_upload(fdtd_ctx *c, const fdtd_fields *host)
+static size_t slab_offset(const fdtd_ctx *c, int idx, bool whole_cavity)
+{
+    const DenseShape s = dense_shape(c->p, idx);
+    return whole_cavity ? c->k0 * s.w * s.h : 0;
+}
+
+static int upload_impl(fdtd_ctx *c, const fdtd_fields *host, bool whole_cavity);
+static int download_impl(fdtd_ctx *c, const fdtd_fields *host, bool whole_cavity);
+
+int fdtd_upload(fdtd_ctx *c, const fdtd_fields *host) { return upload_impl(c, host, true); }
+int fdtd_download(fdtd_ctx *c, const fdtd_fields *host) { return download_impl(c, host, true); }
+int fdtd_upload_slab(fdtd_ctx *c, const fdtd_fields *host) { return upload_impl(c, host, false); }
+int fdtd_download_slab(fdtd_ctx *c, const fdtd_fields *host) { return download_impl(c, host, false); }
+
+static int upload_impl(fdtd_ctx *c, const fdtd_fields *host, bool whole_cavity)
 {
     FDTD_TRY(check_ctx(c, "fdtd_upload"));
     if (!host || !host->Ex || !host->Ey || !host->Ez || !host->Hx || !host->Hy || !host->Hz) {
@@ -745,12 +817,12 @@ int fdtd_upload(fdtd_ctx *c, const fdtd_fields *host)
     FDTD_TRY(use_device(c));
     double *h[6] = {host->Ex, host->Ey, host->Ez, host->Hx, host->Hy, host->Hz};
     for (int a = 0; a < 6; ++a)
-        FDTD_TRY(copy_field(c, a, h[a], true));
+        FDTD_TRY(copy_field(c, a, h[a] + slab_offset(c, a, whole_cavity), true));
     c->e_halo_valid = c->h_halo_valid = (c->nranks == 1);
     return FDTD_OK;
 }
 
-int fdtd_download(fdtd_ctx *c, const fdtd_fields *host)
+static int download_impl(fdtd_ctx *c, const fdtd_fields *host, bool whole_cavity)
 {
     FDTD_TRY(check_ctx(c, "fdtd_download"));
     if (!host || !host->Ex || !host->Ey || !host->Ez || !host->Hx || !host->Hy || !host->Hz) {
@@ -760,7 +832,7 @@ int fdtd_download(fdtd_ctx *c, const fdtd_fields *host)
     FDTD_TRY(use_device(c));
     double *h[6] = {host->Ex, host->Ey, host->Ez, host->Hx, host->Hy, host->Hz};
     for (int a = 0; a < 6; ++a)
-        FDTD_TRY(copy_field(c, a, h[a], false));
+        FDTD_TRY(copy_field(c, a, h[a] + slab_offset(c, a, whole_cavity), false));
     CUDA_TRY(cudaStreamSynchronize(c->s_main));
     return FDTD_OK;
 }
@@ -778,7 +850,7 @@ int fdtd_set_initial_conditions(fdtd_ctx *c)
     }
     int rc = fdtd_initial_conditions_host(&c->p, ey);
     if (rc == FDTD_OK)
-        rc = copy_field(c, 1, ey, true);
+        rc = copy_field(c, 1, ey + slab_offset(c, 1, true), true);
     if (rc == FDTD_OK && cudaStreamSynchronize(c->s_main) != cudaSuccess) {
         fdtd_set_error("fdtd_set_initial_conditions: upload failed");
         rc = FDTD_E_CUDA;

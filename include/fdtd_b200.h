@@ -108,7 +108,8 @@ int fdtd_nccl_unique_id(void *id128);
 int fdtd_ctx_comm_init(fdtd_ctx *ctx, const void *id128);
 
 /* Tunables: "kernel" (0 = one thread per cell, 1 = z-marching register strips),
- * "strip" rows per thread, "kchunk" planes per block, "warps_x", "warps_y". */
+ * "strip" rows per thread, "kchunk" planes per block, "warps_x", "warps_y".
+ * Read-only: "k0", "k1" (owned cell planes), "launches" (kernels launched by this library). */
 int fdtd_ctx_set_option(fdtd_ctx *ctx, const char *key, long value);
 int fdtd_ctx_get_option(fdtd_ctx *ctx, const char *key, long *value);
 
@@ -116,6 +117,11 @@ int fdtd_ctx_get_option(fdtd_ctx *ctx, const char *key, long *value);
  * the WHOLE cavity; a slab context copies only the planes it owns. */
 int fdtd_upload(fdtd_ctx *ctx, const fdtd_fields *host);
 int fdtd_download(fdtd_ctx *ctx, const fdtd_fields *host);
+/* Same, but the pointers address dense arrays holding ONLY this slab's planes: cell planes
+ * [k0,k1) for Ez, Hx, Hy; node planes [k0,k1) -- plus plane maxk on the last slab -- for Ex, Ey, Hz.
+ * (No host has room for a whole 2048^3 cavity.) */
+int fdtd_upload_slab(fdtd_ctx *ctx, const fdtd_fields *host);
+int fdtd_download_slab(fdtd_ctx *ctx, const fdtd_fields *host);
 /* set_initial_conditions(), main.c:416-424, applied to the device Ey. */
 int fdtd_set_initial_conditions(fdtd_ctx *ctx);
 

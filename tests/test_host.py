@@ -1,0 +1,116 @@
+"""Host half of the product (no GPU): the C ABI loads and exports every declared symbol, and the
+host-side functions of the path agree with the oracle bit for bit."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, bits_equal, to_oracle_params
+
+
+def test_library_exports_every_declared_symbol(F):
+    header = open(os.path.join(ROOT, "include", "fdtd_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(fdtd_[a-z_A-Z0-9]+)\s*\(", header))
+    declared -= {"fdtd_dump_sink"}
+    assert len(declared) >= 30
+    for name in sorted(declared):
+        assert hasattr(F.lib, name), f"{name} is declared in include/fdtd_b200.h but not exported"
+    assert set(F.SIGNATURES) == declared
+    assert F.lib.fdtd_abi_version() == 1
+
+
+def test_no_silent_cpu_path(F):
+    """Without a CUDA device every device entry point must fail loudly, never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    p = F.make_params(0.05, 0.05, 0.05, 0.001, 6e-13, 1.2e-10, 2, 1)
+    with pytest.raises(F.FdtdError) as e:
+        F.Context(p)
+    assert e.value.code == -3  # FDTD_E_CUDA
+
+
+def test_load_parameters_matches_oracle(F, oracle, tmp_path):
+    o = oracle.restatement()
+    cases = [oracle.STOCK_PARAMS,
+             ("0.05", "0.04", "0.03", "0.001", "0.0000000000006", "0.00000000012", "2", "1"),
+             ("1.024", "1.024", "1.024", "0.001", "6e-13", "6e-11", "50", "1"),
+             ("0.256", "0.256", "0.256", "0.001", "0.0000000000006", "0.0000000006", "1000000", "1")]
+    for nums in cases:
+        path = oracle.write_params(tmp_path / "p.txt", nums)
+        a, b = F.load_parameters(path), o.load_parameters(path)
+        assert a.dims() == b.dims()
+        for name in ("length", "width", "height", "spatial_step", "time_step", "simulation_time",
+                     "sampling_rate", "mode"):
+            assert getattr(a, name) == getattr(b, name), name
+        assert F.step_count(a) == oracle.step_count(b)
+        want = oracle.field_shapes(*b.dims())
+        assert F.field_sizes(a) == [int(np.prod(want[k])) for k in oracle.FIELD_NAMES]
+    with pytest.raises(F.FdtdError) as e:
+        F.load_parameters(tmp_path / "missing.txt")
+    assert e.value.code == -2 and "Unable to open parameters file!" in str(e.value)
+
+
+@pytest.mark.parametrize("dims", [(0.05, 0.05, 0.05), (0.05, 0.04, 0.03), (0.256, 0.256, 0.256),
+                                  (0.037, 0.029, 0.023)])
+def test_source_values_match_oracle_set_source(F, oracle, dims):
+    """fdtd_source_values == what set_source (main.c:748,751) writes, at several times."""
+    o = oracle.restatement()
+    p = F.make_params(*dims, 0.001, 6e-13, 1.2e-10, 2, 1)
+    q = to_oracle_params(oracle, p)
+    plan = F.source_plan(p)
+    assert (plan.i0, plan.i1, plan.j0, plan.j1) == oracle.source_bounds(q)
+    assert plan.z_te == oracle.source_zte(q)
+    if max(q.dims()) > 64:
+        q = oracle.make_params(*dims[:2], 0.002, 0.001, 6e-13, 1.2e-10, 2, 1)  # thin z: same patch
+    for t in (0.0, 6e-13, 7 * 6e-13, 1.19994e-10):
+        f = oracle.alloc_fields(*q.dims())
+        o.set_source(q, f, t)
+        ez, hx = F.source_values(p, plan, t)
+        for s in range(plan.i1 - plan.i0):
+            col_e = f["ez"][0, plan.j0:plan.j1, plan.i0 + s]
+            col_h = f["hx"][0, plan.j0:plan.j1, plan.i0 + s]
+            assert bits_equal(col_e, np.full_like(col_e, ez[s]))
+            assert bits_equal(col_h, np.full_like(col_h, hx[s]))
+
+
+def test_initial_conditions_match_oracle(F, oracle):
+    o = oracle.restatement()
+    for dims in ((0.05, 0.05, 0.05), (0.033, 0.017, 0.009)):
+        p = F.make_params(*dims, 0.001, 6e-13, 1.2e-10, 2, 0)
+        q = to_oracle_params(oracle, p)
+        f = oracle.alloc_fields(*q.dims())
+        o.set_initial_conditions(q, f)
+        assert bits_equal(F.initial_conditions_host(p), f["ey"])
+
+
+def test_slab_ranges_partition_the_planes(F):
+    for maxk in (1, 7, 50, 256, 1024, 2048):
+        for n in (1, 2, 3, 4, 8):
+            if n > maxk:
+                with pytest.raises(F.FdtdError):
+                    r = [F.slab_range(maxk, k, n) for k in range(n)]
+                    if any(a == b for a, b in r):
+                        raise F.FdtdError(-1, "empty slab")
+                continue
+            r = [F.slab_range(maxk, k, n) for k in range(n)]
+            assert r[0][0] == 0 and r[-1][1] == maxk
+            assert all(r[k][1] == r[k + 1][0] for k in range(n - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    with pytest.raises(F.FdtdError):
+        F.slab_range(10, 3, 3)
+
+
+def test_pattern_and_checksum_mirrors_are_consistent(F):
+    p = F.make_params(0.009, 0.007, 0.005, 0.001, 6e-13, 1.2e-10, 2, 0)
+    a = F.pattern_host(p, 42)
+    b = F.pattern_host(p, 43)
+    assert all(abs(v).max() < 1.0 for v in a.values())
+    assert F.checksum_host(a) != F.checksum_host(b)
+    c = {k: v.copy() for k, v in a.items()}
+    c["Hy"][1, 2, 3], c["Hy"][1, 2, 2] = c["Hy"][1, 2, 2], c["Hy"][1, 2, 3]  # a swap must show
+    assert F.checksum_host(c)[4] != F.checksum_host(a)[4]
+    assert F.checksum_host(c)[:4] == F.checksum_host(a)[:4]

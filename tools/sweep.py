@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""Kernel-variant sweep on one GPU: Gcell-updates/s and per-kernel GB/s for each launch shape.
+    python tools/sweep.py [--nz 512] [--steps 5]  > gpurun_out/sweep.txt
+"""
+import argparse
+import itertools
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import fdtd_b200 as F  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=1024)
+ap.add_argument("--nz", type=int, default=512)
+ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--quick", action="store_true")
+args = ap.parse_args()
+
+p = F.make_params(args.n * 1e-3, args.n * 1e-3, args.nz * 1e-3, 1e-3, 6e-13, 1e-9, 1 << 30, 1)
+assert p.dims() == (args.n, args.n, args.nz), p.dims()
+cells = args.n * args.n * args.nz
+variants = [dict(kernel=0)]
+shapes = [(1, 8), (2, 4), (4, 2), (8, 1), (1, 4), (2, 2), (4, 1)]
+for strip, kchunk, (wx, wy) in itertools.product((1, 2, 4), (8, 32, 128), shapes):
+    if args.quick and (kchunk != 32 or (wx, wy) not in ((2, 4), (4, 2))):
+        continue
+    variants.append(dict(kernel=1, strip=strip, kchunk=kchunk, warps_x=wx, warps_y=wy))
+
+ref_sum = None
+with F.Context(p) as ctx:
+    for v in variants:
+        for k, val in v.items():
+            ctx.set_option(k, val)
+        ctx.fill_test_pattern(1)
+        t = ctx.run(2, 0.0)
+        ctx.sync()
+        t, total, h, e = ctx.run_timed(args.steps, t)
+        s = ctx.checksum()
+        if ref_sum is None:
+            ref_sum = s
+        ok = s == ref_sum
+        gcs = cells * args.steps / (total * 1e-3) / 1e9
+        hb = 72.0 * cells / (h / args.steps * 1e-3) / 1e9
+        eb = 72.0 * cells / (e / args.steps * 1e-3) / 1e9
+        print(json.dumps(dict(v, gcell_s=round(gcs, 2), h_gbs=round(hb), e_gbs=round(eb), same_bits=ok)), flush=True)
