@@ -182,6 +182,19 @@ def nccl_unique_id() -> bytes:
     return buf.raw
 
 
+# The halo plan implemented by exchange_h / exchange_e in csrc/fdtd_ctx.cu, spelled
+# out so the CPU tests can run the same plan over gloo with the oracle as the per-slab kernel:
+# after each half-step one plane of two components travels to one neighbour.
+HALO_PLAN = {
+    # after update_H_field: my top owned CELL plane (k1-1) of Hx, Hy goes to rank+1, which keeps it
+    # as its plane k0-1 (read by its Ex/Ey update at node plane k0, main.c:486-493)
+    "after_H": {"fields": ("Hx", "Hy"), "send_plane": "k1-1", "to": +1, "recv_plane": "k0-1"},
+    # after update_E_field: my first owned NODE plane (k0) of Ex, Ey goes to rank-1, which keeps it
+    # as its plane k1 (read by its Hx/Hy update at cell plane k1-1, main.c:448-455)
+    "after_E": {"fields": ("Ex", "Ey"), "send_plane": "k0", "to": -1, "recv_plane": "k1"},
+}
+
+
 class PinnedArrays:
     """Six pinned host arrays in the reference's dense layout (fdtd_host_alloc)."""
 

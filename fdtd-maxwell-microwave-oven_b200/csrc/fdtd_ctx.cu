@@ -147,6 +147,10 @@ int check_ctx(const fdtd_ctx *c, const char *who)
         fdtd_set_error("%s: context is NULL", who);
         return FDTD_E_ARG;
     }
+    if (c->opt_wx * c->opt_wy > 8) { /* a block is at most 256 threads */
+        fdtd_set_error("%s: options warps_x (%ld) * warps_y (%ld) must be <= 8", who, c->opt_wx, c->opt_wy);
+        return FDTD_E_ARG;
+    }
     return FDTD_OK;
 }
 
@@ -738,7 +742,10 @@ int fdtd_ctx_comm_init(fdtd_ctx *c, const void *id128)
 
 int fdtd_ctx_set_option(fdtd_ctx *c, const char *key, long value)
 {
-    FDTD_TRY(check_ctx(c, "fdtd_ctx_set_option"));
+    if (!c) {
+        fdtd_set_error("fdtd_ctx_set_option: context is NULL");
+        return FDTD_E_ARG;
+    }
     if (!key) {
         fdtd_set_error("fdtd_ctx_set_option: NULL key");
         return FDTD_E_ARG;
@@ -750,12 +757,6 @@ int fdtd_ctx_set_option(fdtd_ctx *c, const char *key, long value)
     else if (!strcmp(key, "warps_y") && value >= 1 && value <= 8) c->opt_wy = value;
     else {
         fdtd_set_error("fdtd_ctx_set_option: unknown key or bad value: %s = %ld", key, value);
-        return FDTD_E_ARG;
-    }
-    if (c->opt_wx * c->opt_wy > 8) {
-        fdtd_set_error("fdtd_ctx_set_option: warps_x * warps_y must be <= 8");
-        c->opt_wx = 2;
-        c->opt_wy = 4;
         return FDTD_E_ARG;
     }
     return FDTD_OK;
