@@ -249,7 +249,8 @@ def main():
     alg_bytes = BYTES_PER_CELL_HALF_STEP * cells_local
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": TRAFFIC_BYTES_PER_LAUNCH,
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": TRAFFIC_BYTES_PER_CELL_HALF_STEP * cells_local,
+                "traffic_source": TRAFFIC_SOURCE,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": dom_ms,
                 "h_ms_per_step": h_ms / K, "e_ms_per_step": e_ms / K,
                 "step_frac_of_roofline": (2 * alg_bytes / (total_ms / K * 1e-3) / 1e9) / peak}
@@ -303,9 +304,11 @@ def main():
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel at the
-# 1024^3 workload, from the ncu --set full capture under profiles/ (None until captured)
-TRAFFIC_BYTES_PER_LAUNCH = None
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, per cell, from
+# the ncu --set full capture under profiles/ (taken at 1024 x 1024 x 256 cells so that ncu's
+# save/restore of the state stays small; per-cell traffic does not depend on the plane count)
+TRAFFIC_BYTES_PER_CELL_HALF_STEP = 20.022561e9 / (1024 * 1024 * 256)
+TRAFFIC_SOURCE = "profiles/r01_split_ncu_full_raw.csv (k_update_h_march<2>, 20.02 GB per launch at 1024x1024x256)"
 
 if __name__ == "__main__":
     main()

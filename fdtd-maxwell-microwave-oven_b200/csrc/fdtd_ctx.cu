@@ -591,10 +591,10 @@ int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx
     c->ch = fdtd_factor_h(p);
     c->ce = fdtd_factor_e(p);
     c->opt_kernel = 1;
-    c->opt_strip = 4;
-    c->opt_kchunk = 32;
+    c->opt_strip = 2;
+    c->opt_kchunk = 8;
     c->opt_wx = 2;
-    c->opt_wy = 4;
+    c->opt_wy = 2;
 
     rc = fdtd_source_plan_make(p, &c->plan);
     if (rc != FDTD_OK) {
@@ -1052,7 +1052,8 @@ void *writer_main(void *arg)
             dp->error = err;
             snprintf(dp->error_msg, sizeof dp->error_msg, "dump of iteration %d failed in %s", iteration, what);
         }
-        dp->scratch_busy = false;
+        /* scratch_busy was released when the last variable left HBM; by now the compute thread may
+         * already own the scratch again for the next dump, so it must not be touched here */
         pthread_cond_broadcast(&dp->cv);
         pthread_mutex_unlock(&dp->mu);
     }
@@ -1103,20 +1104,27 @@ int pipe_create(fdtd_ctx *c, const fdtd_dump_sink *sink)
     return FDTD_OK;
 }
 
+/* let the writer finish what is queued, then stop it */
+void pipe_join(DumpPipe *dp)
+{
+    if (!dp->thread)
+        return;
+    pthread_mutex_lock(&dp->mu);
+    dp->stop = true;
+    pthread_cond_broadcast(&dp->cv);
+    pthread_mutex_unlock(&dp->mu);
+    pthread_join(dp->thread, nullptr);
+    dp->thread = 0;
+    pthread_mutex_destroy(&dp->mu);
+    pthread_cond_destroy(&dp->cv);
+}
+
 void pipe_destroy(fdtd_ctx *c)
 {
     DumpPipe *dp = c->pipe;
     if (!dp)
         return;
-    if (dp->thread) {
-        pthread_mutex_lock(&dp->mu);
-        dp->stop = true;
-        pthread_cond_broadcast(&dp->cv);
-        pthread_mutex_unlock(&dp->mu);
-        pthread_join(dp->thread, nullptr);
-        pthread_mutex_destroy(&dp->mu);
-        pthread_cond_destroy(&dp->cv);
-    }
+    pipe_join(dp);
     for (int v = 0; v < 7; ++v)
         if (dp->dev[v]) cudaFree(dp->dev[v]);
     for (int b = 0; b < 2; ++b) {
@@ -1224,15 +1232,12 @@ int fdtd_propagate(fdtd_ctx *c, const fdtd_dump_sink *sink, size_t *steps_done, 
         rc = fdtd_sync(c);
     if (c->pipe) {
         DumpPipe *dp = c->pipe;
-        pthread_mutex_lock(&dp->mu);
-        while ((dp->scratch_busy || dp->pending_iteration >= 0) && !dp->error)
-            pthread_cond_wait(&dp->cv, &dp->mu);
+        pipe_join(dp); /* returns after the last sink.end() */
         if (dp->error && rc == FDTD_OK) {
             rc = dp->error;
             fdtd_set_error("%s", dp->error_msg);
         }
-        pthread_mutex_unlock(&dp->mu);
-        pipe_destroy(c); /* joins the writer after its last sink.end() */
+        pipe_destroy(c);
     }
     if (steps_done) *steps_done = steps;
     if (time_counter) *time_counter = t;
