@@ -8,6 +8,7 @@
  */
 #include "fdtd_internal.h"
 #include "fdtd_kernels.cuh"
+#include "fdtd_fused.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -108,13 +109,17 @@ struct fdtd_ctx {
     size_t k0, k1;
     Geo g;
     Fld f;
-    double *base;       /* one allocation holding the six arrays */
+    double *base;       /* the six arrays of the current state, inside raw (guard margins either side) */
+    double *base2;      /* second set for the fused single-sweep step ("kernel" = 2), allocated on demand */
+    double *raw, *raw2; /* what cudaMalloc returned */
+    Fld f2;
     size_t array_elems; /* P * R * planes */
     double ch, ce;      /* update factors, main.c:441 / :479 */
 
     cudaStream_t s_main, s_comm, s_dump;
     cudaEvent_t ev_hb, ev_eb, ev_hhalo, ev_ehalo;
     bool e_halo_valid, h_halo_valid;
+    bool low_e_halo_valid; /* fused step only: plane 0 also holds the lower neighbour's Ex, Ey, Ez */
     ncclComm_t comm;
     bool has_comm;
 
@@ -128,7 +133,7 @@ struct fdtd_ctx {
     double *src_one_dev; /* single row for the operator-level fdtd_set_source */
 
     /* options */
-    long opt_kernel, opt_strip, opt_kchunk, opt_wx, opt_wy;
+    long opt_kernel, opt_strip, opt_kchunk, opt_wx, opt_wy, opt_prefetch;
     mutable long launches; /* kernels of this library launched so far (reports) */
 
     /* dump scratch for fdtd_aggregate */
@@ -234,7 +239,7 @@ template <int TY>
 void launch_h_march_t(const fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStream_t st)
 {
     const int wx = (int)c->opt_wx, wy = (int)c->opt_wy;
-    Span sp{kl_begin, kl_end, (int)c->opt_kchunk};
+    Span sp{kl_begin, kl_end, (int)c->opt_kchunk, (int)c->opt_prefetch};
     dim3 block(32 * wx, wy);
     dim3 grid((c->g.I + 1 + block.x - 1) / block.x, (c->g.J + 1 + wy * TY - 1) / (wy * TY),
               (kl_end - kl_begin + sp.kchunk - 1) / sp.kchunk);
@@ -246,7 +251,7 @@ template <int TY>
 void launch_e_march_t(const fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStream_t st)
 {
     const int wx = (int)c->opt_wx, wy = (int)c->opt_wy;
-    Span sp{kl_begin, kl_end, (int)c->opt_kchunk};
+    Span sp{kl_begin, kl_end, (int)c->opt_kchunk, (int)c->opt_prefetch};
     dim3 block(32 * wx, wy);
     dim3 grid((c->g.I + 1 + block.x - 1) / block.x, (c->g.J + 1 + wy * TY - 1) / (wy * TY),
               (kl_end - kl_begin + sp.kchunk - 1) / sp.kchunk);
@@ -275,8 +280,8 @@ void launch_h(const fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStr
     }
     switch (c->opt_strip) {
     case 1: launch_h_march_t<1>(c, s, kl_begin, kl_end, st); break;
-    case 2: launch_h_march_t<2>(c, s, kl_begin, kl_end, st); break;
-    default: launch_h_march_t<4>(c, s, kl_begin, kl_end, st); break;
+    case 4: launch_h_march_t<4>(c, s, kl_begin, kl_end, st); break;
+    default: launch_h_march_t<2>(c, s, kl_begin, kl_end, st); break;
     }
 }
 
@@ -299,8 +304,83 @@ void launch_e(const fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStr
     }
     switch (c->opt_strip) {
     case 1: launch_e_march_t<1>(c, s, kl_begin, kl_end, st); break;
-    case 2: launch_e_march_t<2>(c, s, kl_begin, kl_end, st); break;
-    default: launch_e_march_t<4>(c, s, kl_begin, kl_end, st); break;
+    case 4: launch_e_march_t<4>(c, s, kl_begin, kl_end, st); break;
+    default: launch_e_march_t<2>(c, s, kl_begin, kl_end, st); break;
+    }
+}
+
+/* Guard margins of a state allocation, in doubles.  The fused kernel loads without predicates
+ * (fdtd_fused.cuh): a thread of an edge block may read up to one row and one column before the
+ * first array and up to two planes and a few rows past the last one.  Those values are never
+ * used for a stored result; the margins only keep the addresses inside the allocation. */
+size_t margin_front(const fdtd_ctx *c) { return (size_t)c->g.P + 64; }
+size_t margin_back(const fdtd_ctx *c) { return 2 * (size_t)c->g.PR + 8 * (size_t)c->g.P + 1024; }
+
+/* one zero-filled set of six arrays (padding must be zero and stays zero) */
+cudaError_t alloc_state(fdtd_ctx *c, double **raw, double **base)
+{
+    const size_t n = margin_front(c) + 6 * c->array_elems + margin_back(c);
+    cudaError_t e = cudaMalloc((void **)raw, n * sizeof(double));
+    if (e != cudaSuccess) {
+        *raw = nullptr;
+        return e;
+    }
+    *base = *raw + margin_front(c);
+    return cudaMemsetAsync(*raw, 0, n * sizeof(double), c->s_main);
+}
+
+/* second buffer set of the fused step */
+int ensure_pong(fdtd_ctx *c)
+{
+    if (c->base2)
+        return FDTD_OK;
+    cudaError_t e = alloc_state(c, &c->raw2, &c->base2);
+    if (e != cudaSuccess) {
+        c->base2 = nullptr;
+        fdtd_set_error("fused step needs a second copy of the state (%zu bytes): %s",
+                       6 * c->array_elems * sizeof(double), cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? FDTD_E_NOMEM : FDTD_E_CUDA;
+    }
+    double **p2[6] = {&c->f2.ex, &c->f2.ey, &c->f2.ez, &c->f2.hx, &c->f2.hy, &c->f2.hz};
+    for (int a = 0; a < 6; ++a)
+        *p2[a] = c->base2 + (size_t)a * c->array_elems;
+    return FDTD_OK;
+}
+
+void swap_buffers(fdtd_ctx *c)
+{
+    std::swap(c->raw, c->raw2);
+    std::swap(c->base, c->base2);
+    std::swap(c->f, c->f2);
+}
+
+template <int TY>
+void launch_fused_t(const fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStream_t st)
+{
+    /* 128 threads per block; a chunk shorter than 2 planes would put the source plane into a
+     * chunk's "H only" prologue for no gain */
+    int wx = (int)c->opt_wx, wy = (int)c->opt_wy;
+    while (wx * wy > 4) {
+        if (wy > 1) wy /= 2; else wx /= 2;
+    }
+    Span sp{kl_begin, kl_end, (int)std::max(c->opt_kchunk, 2L), (int)c->opt_prefetch};
+    dim3 block(32 * wx, wy);
+    dim3 grid((c->g.I + 1 + block.x - 1) / block.x, (c->g.J + 1 + wy * TY - 1) / (wy * TY),
+              (kl_end - kl_begin + sp.kchunk - 1) / sp.kchunk);
+    k_step_fused<TY><<<grid, block, 0, st>>>(c->g, c->f, c->f2, c->ch, c->ce, s, sp);
+    ++c->launches;
+}
+
+/* one whole step (H then E) of the local planes [kl_begin, kl_end): reads c->f, writes c->f2 */
+void launch_fused(const fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStream_t st)
+{
+    if (kl_end <= kl_begin)
+        return;
+    switch (c->opt_strip) {
+    case 1: launch_fused_t<1>(c, s, kl_begin, kl_end, st); break;
+    case 3: launch_fused_t<3>(c, s, kl_begin, kl_end, st); break;
+    case 4: launch_fused_t<4>(c, s, kl_begin, kl_end, st); break;
+    default: launch_fused_t<2>(c, s, kl_begin, kl_end, st); break;
     }
 }
 
@@ -315,8 +395,10 @@ void launch_set_source(const fdtd_ctx *c, const double *row_dev, cudaStream_t st
 
 /* ---- halo exchange (one plane each way per half-step) ----------------------- */
 
-/* Hx, Hy of my top cell plane go up; the lower neighbour's arrive in my plane 0. */
-int exchange_h(fdtd_ctx *c, cudaStream_t st)
+/* Hx, Hy of my top cell plane go up; the lower neighbour's arrive in my plane 0.
+ * with_e: also Ex, Ey, Ez of that plane -- the fused step recomputes H of the plane below its
+ * slab and needs the E around it (fdtd_fused.cuh). */
+int exchange_h(fdtd_ctx *c, cudaStream_t st, bool with_e)
 {
     if (c->nranks == 1)
         return FDTD_OK;
@@ -325,15 +407,15 @@ int exchange_h(fdtd_ctx *c, cudaStream_t st)
         return FDTD_E_STATE;
     }
     const size_t n = (size_t)c->g.PR;
+    double *up[5] = {c->f.hx, c->f.hy, c->f.ex, c->f.ey, c->f.ez};
+    const int count = with_e ? 5 : 2;
     NCCL_TRY(g_nccl.GroupStart());
-    if (c->rank + 1 < c->nranks) {
-        NCCL_TRY(g_nccl.Send(c->f.hx + n * c->g.nk, n, ncclDouble, c->rank + 1, c->comm, st));
-        NCCL_TRY(g_nccl.Send(c->f.hy + n * c->g.nk, n, ncclDouble, c->rank + 1, c->comm, st));
-    }
-    if (c->rank > 0) {
-        NCCL_TRY(g_nccl.Recv(c->f.hx, n, ncclDouble, c->rank - 1, c->comm, st));
-        NCCL_TRY(g_nccl.Recv(c->f.hy, n, ncclDouble, c->rank - 1, c->comm, st));
-    }
+    if (c->rank + 1 < c->nranks)
+        for (int a = 0; a < count; ++a)
+            NCCL_TRY(g_nccl.Send(up[a] + n * c->g.nk, n, ncclDouble, c->rank + 1, c->comm, st));
+    if (c->rank > 0)
+        for (int a = 0; a < count; ++a)
+            NCCL_TRY(g_nccl.Recv(up[a], n, ncclDouble, c->rank - 1, c->comm, st));
     NCCL_TRY(g_nccl.GroupEnd());
     return FDTD_OK;
 }
@@ -366,18 +448,22 @@ int exchange_e(fdtd_ctx *c, cudaStream_t st, bool with_hz)
     return FDTD_OK;
 }
 
-/* make both halos current on the compute stream (after upload / operator-level calls) */
+/* make the halos the selected kernel needs current, on the compute stream (after upload /
+ * operator-level calls).  The flags are set identically on every rank, so the sends and
+ * receives always pair up. */
 int refresh_halos(fdtd_ctx *c)
 {
     if (c->nranks == 1)
         return FDTD_OK;
+    const bool fused = c->opt_kernel == 2;
     if (!c->e_halo_valid) {
         FDTD_TRY(exchange_e(c, c->s_main, false));
         c->e_halo_valid = true;
     }
-    if (!c->h_halo_valid) {
-        FDTD_TRY(exchange_h(c, c->s_main));
+    if (!c->h_halo_valid || (fused && !c->low_e_halo_valid)) {
+        FDTD_TRY(exchange_h(c, c->s_main, fused));
         c->h_halo_valid = true;
+        c->low_e_halo_valid = fused;
     }
     return FDTD_OK;
 }
@@ -391,6 +477,48 @@ int queue_step(fdtd_ctx *c, const Src &s, cudaEvent_t ev_h_begin, cudaEvent_t ev
     const int h_end = nk + c->g.top + 1; /* exclusive */
     if (ev_h_begin)
         CUDA_TRY(cudaEventRecord(ev_h_begin, c->s_main));
+
+    if (c->opt_kernel == 2) {
+        /* fused: one sweep does H and E; reads c->f, writes c->f2, then the two swap */
+        if (c->nranks == 1) {
+            launch_fused(c, s, 1, h_end, c->s_main);
+            swap_buffers(c);
+        } else {
+            CUDA_TRY(cudaStreamWaitEvent(c->s_main, c->ev_ehalo, 0));
+            CUDA_TRY(cudaStreamWaitEvent(c->s_main, c->ev_hhalo, 0));
+            const bool sends_up = c->rank + 1 < c->nranks, sends_down = c->rank > 0;
+            if (nk < 3) {
+                launch_fused(c, s, 1, h_end, c->s_main);
+            } else {
+                int lo = 1, hi = h_end;
+                if (sends_up) { /* top owned plane first: 5 arrays of it travel up */
+                    launch_fused(c, s, nk, nk + 1, c->s_main);
+                    hi = nk;
+                }
+                if (sends_down) { /* first owned plane: Ex, Ey travel down */
+                    launch_fused(c, s, 1, 2, c->s_main);
+                    lo = 2;
+                }
+                CUDA_TRY(cudaEventRecord(c->ev_hb, c->s_main));
+                launch_fused(c, s, lo, hi, c->s_main);
+            }
+            if (nk < 3)
+                CUDA_TRY(cudaEventRecord(c->ev_hb, c->s_main));
+            swap_buffers(c); /* the exchange below works on the new state */
+            CUDA_TRY(cudaStreamWaitEvent(c->s_comm, c->ev_hb, 0));
+            FDTD_TRY(exchange_h(c, c->s_comm, true));
+            FDTD_TRY(exchange_e(c, c->s_comm, false));
+            CUDA_TRY(cudaEventRecord(c->ev_hhalo, c->s_comm));
+            CUDA_TRY(cudaEventRecord(c->ev_ehalo, c->s_comm));
+        }
+        if (ev_mid)
+            CUDA_TRY(cudaEventRecord(ev_mid, c->s_main));
+        if (ev_e_end)
+            CUDA_TRY(cudaEventRecord(ev_e_end, c->s_main));
+        CUDA_TRY(cudaGetLastError());
+        return FDTD_OK;
+    }
+
     if (c->opt_kernel == 0 && c->src_here)
         launch_set_source(c, s.vals, c->s_main);
     if (c->nranks == 1) {
@@ -407,7 +535,7 @@ int queue_step(fdtd_ctx *c, const Src &s, cudaEvent_t ev_h_begin, cudaEvent_t ev
             CUDA_TRY(cudaEventRecord(c->ev_hb, c->s_main));
         }
         CUDA_TRY(cudaStreamWaitEvent(c->s_comm, c->ev_hb, 0));
-        FDTD_TRY(exchange_h(c, c->s_comm));
+        FDTD_TRY(exchange_h(c, c->s_comm, false));
         CUDA_TRY(cudaEventRecord(c->ev_hhalo, c->s_comm));
     }
     if (ev_mid)
@@ -434,6 +562,7 @@ int queue_step(fdtd_ctx *c, const Src &s, cudaEvent_t ev_h_begin, cudaEvent_t ev
     if (ev_e_end)
         CUDA_TRY(cudaEventRecord(ev_e_end, c->s_main));
     CUDA_TRY(cudaGetLastError());
+    c->low_e_halo_valid = false; /* the split kernels refresh only Hx, Hy of plane 0 */
     return FDTD_OK;
 }
 
@@ -461,6 +590,8 @@ int stage_source_rows(fdtd_ctx *c, size_t count, double *t_io)
 int run_impl(fdtd_ctx *c, size_t steps, double *time_counter, float *total_ms, float *h_ms, float *e_ms)
 {
     FDTD_TRY(use_device(c));
+    if (c->opt_kernel == 2)
+        FDTD_TRY(ensure_pong(c));
     FDTD_TRY(refresh_halos(c));
     if (c->nranks > 1) {
         /* the first step's waits need recorded events */
@@ -628,7 +759,8 @@ int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx
     } while (0)
 
     CREATE_TRY(cudaSetDevice(device));
-    CREATE_TRY(cudaMalloc((void **)&c->base, 6 * c->array_elems * sizeof(double)));
+    CREATE_TRY(cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking));
+    CREATE_TRY(alloc_state(c, &c->raw, &c->base)); /* initialize_fields(), main.c:294-364: all zero */
     c->f.ex = field_ptr(c, 0);
     c->f.ey = field_ptr(c, 1);
     c->f.ez = field_ptr(c, 2);
@@ -637,7 +769,6 @@ int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx
     c->f.hz = field_ptr(c, 5);
     int lo = 0, hi = 0;
     CREATE_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    CREATE_TRY(cudaStreamCreateWithPriority(&c->s_main, cudaStreamNonBlocking, lo));
     CREATE_TRY(cudaStreamCreateWithPriority(&c->s_comm, cudaStreamNonBlocking, hi));
     CREATE_TRY(cudaStreamCreateWithPriority(&c->s_dump, cudaStreamNonBlocking, lo));
     CREATE_TRY(cudaEventCreateWithFlags(&c->ev_hb, cudaEventDisableTiming));
@@ -645,8 +776,6 @@ int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx
     CREATE_TRY(cudaEventCreateWithFlags(&c->ev_hhalo, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&c->ev_ehalo, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&c->ev_src, cudaEventDisableTiming));
-    /* initialize_fields(), main.c:294-364: all zero */
-    CREATE_TRY(cudaMemsetAsync(c->base, 0, 6 * c->array_elems * sizeof(double), c->s_main));
     const size_t src_row = 2 * (size_t)std::max(c->src_n, 1);
     CREATE_TRY(cudaMalloc((void **)&c->src_dev, kSrcRing * src_row * sizeof(double)));
     CREATE_TRY(cudaMalloc((void **)&c->src_one_dev, src_row * sizeof(double)));
@@ -654,7 +783,7 @@ int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx
     CREATE_TRY(cudaEventRecord(c->ev_src, c->s_main));
     CREATE_TRY(cudaStreamSynchronize(c->s_main));
 #undef CREATE_TRY
-    c->e_halo_valid = c->h_halo_valid = true; /* all zero: halos agree */
+    c->e_halo_valid = c->h_halo_valid = c->low_e_halo_valid = true; /* all zero: halos agree */
     *out = c;
     return FDTD_OK;
 }
@@ -691,7 +820,8 @@ int fdtd_ctx_destroy(fdtd_ctx *c)
     if (c->s_dump) cudaStreamSynchronize(c->s_dump);
     pipe_destroy(c);
     if (c->has_comm) g_nccl.CommDestroy(c->comm);
-    if (c->base) cudaFree(c->base);
+    if (c->raw) cudaFree(c->raw);
+    if (c->raw2) cudaFree(c->raw2);
     if (c->src_dev) cudaFree(c->src_dev);
     if (c->src_one_dev) cudaFree(c->src_one_dev);
     if (c->src_host) cudaFreeHost(c->src_host);
@@ -750,11 +880,12 @@ int fdtd_ctx_set_option(fdtd_ctx *c, const char *key, long value)
         fdtd_set_error("fdtd_ctx_set_option: NULL key");
         return FDTD_E_ARG;
     }
-    if (!strcmp(key, "kernel") && (value == 0 || value == 1)) c->opt_kernel = value;
-    else if (!strcmp(key, "strip") && (value == 1 || value == 2 || value == 4)) c->opt_strip = value;
+    if (!strcmp(key, "kernel") && value >= 0 && value <= 2) c->opt_kernel = value;
+    else if (!strcmp(key, "strip") && value >= 1 && value <= 4) c->opt_strip = value;
     else if (!strcmp(key, "kchunk") && value >= 1 && value <= 1 << 20) c->opt_kchunk = value;
     else if (!strcmp(key, "warps_x") && value >= 1 && value <= 8) c->opt_wx = value;
     else if (!strcmp(key, "warps_y") && value >= 1 && value <= 8) c->opt_wy = value;
+    else if (!strcmp(key, "prefetch") && value >= 0 && value <= 64) c->opt_prefetch = value;
     else {
         fdtd_set_error("fdtd_ctx_set_option: unknown key or bad value: %s = %ld", key, value);
         return FDTD_E_ARG;
@@ -774,6 +905,7 @@ int fdtd_ctx_get_option(fdtd_ctx *c, const char *key, long *value)
     else if (!strcmp(key, "kchunk")) *value = c->opt_kchunk;
     else if (!strcmp(key, "warps_x")) *value = c->opt_wx;
     else if (!strcmp(key, "warps_y")) *value = c->opt_wy;
+    else if (!strcmp(key, "prefetch")) *value = c->opt_prefetch;
     else if (!strcmp(key, "k0")) *value = (long)c->k0;
     else if (!strcmp(key, "k1")) *value = (long)c->k1;
     else if (!strcmp(key, "launches")) *value = c->launches;
@@ -819,7 +951,7 @@ static int upload_impl(fdtd_ctx *c, const fdtd_fields *host, bool whole_cavity)
     double *h[6] = {host->Ex, host->Ey, host->Ez, host->Hx, host->Hy, host->Hz};
     for (int a = 0; a < 6; ++a)
         FDTD_TRY(copy_field(c, a, h[a] + slab_offset(c, a, whole_cavity), true));
-    c->e_halo_valid = c->h_halo_valid = (c->nranks == 1);
+    c->e_halo_valid = c->h_halo_valid = c->low_e_halo_valid = (c->nranks == 1);
     return FDTD_OK;
 }
 
@@ -857,7 +989,7 @@ int fdtd_set_initial_conditions(fdtd_ctx *c)
         rc = FDTD_E_CUDA;
     }
     free(ey);
-    c->e_halo_valid = (c->nranks == 1);
+    c->e_halo_valid = c->low_e_halo_valid = (c->nranks == 1);
     return rc;
 }
 
@@ -870,7 +1002,7 @@ int fdtd_set_source(fdtd_ctx *c, double t)
         return FDTD_E_STATE;
     }
     if (c->nranks > 1)
-        c->h_halo_valid = false; /* Hx of plane k = 0 may be a plane that travels (same on all ranks) */
+        c->h_halo_valid = c->low_e_halo_valid = false; /* plane k = 0 may be a plane that travels (same on all ranks) */
     if (!c->src_here)
         return FDTD_OK; /* the patch lives on the slab that holds k = 0 */
     std::vector<double> row(2 * (size_t)c->src_n);
@@ -901,7 +1033,7 @@ int fdtd_update_E_field(fdtd_ctx *c)
     FDTD_TRY(refresh_halos(c));
     launch_e(c, no_src(), 1, c->g.nk + 1, c->s_main);
     CUDA_TRY(cudaGetLastError());
-    c->e_halo_valid = (c->nranks == 1);
+    c->e_halo_valid = c->low_e_halo_valid = (c->nranks == 1);
     return FDTD_OK;
 }
 
@@ -1267,7 +1399,7 @@ int fdtd_fill_test_pattern(fdtd_ctx *c, unsigned long long seed)
         k_fill_pattern<<<grid, block, 0, c->s_main>>>(c->g, field_ptr(c, a), v, seed, a);
     }
     CUDA_TRY(cudaGetLastError());
-    c->e_halo_valid = c->h_halo_valid = (c->nranks == 1);
+    c->e_halo_valid = c->h_halo_valid = c->low_e_halo_valid = (c->nranks == 1);
     return FDTD_OK;
 }
 

@@ -137,7 +137,14 @@ __global__ void k_set_source(Geo g, Fld f, Src s)
 struct Span {
     int kl_begin, kl_end; /* local planes [kl_begin, kl_end) handled by this launch */
     int kchunk;           /* planes per block */
+    int prefetch;         /* planes ahead to pull into L2 (0 = off) */
 };
+
+/* non-blocking hint: bring the line holding p into L2 (no register, no scoreboard entry) */
+__device__ __forceinline__ void prefetch_l2(const double *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 /* resident blocks per SM the register budget is capped for: 256 threads x 2 blocks x 128 registers
  * fill the register file for TY = 4; shorter strips need fewer registers and fit more blocks */

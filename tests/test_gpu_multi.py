@@ -1,0 +1,121 @@
+"""z-slab decomposition on real GPUs (one process per GPU, NCCL halos): every slab's planes must
+equal the single-domain oracle bit for bit, for the operator-level calls, for fdtd_run (halo
+traffic overlapped with the interior planes) and for the dump variables.  Skipped on a 1-GPU box."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+DX, DT = 0.001, 6e-13
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, dims, mode, steps, variant, ret):
+    import sys
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import fdtd_b200 as F
+    import oracle as O
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.cuda.set_device(rank)
+        nx, ny, nz = dims
+        args = ((nx + .5) * DX, (ny + .5) * DX, (nz + .5) * DX, DX, DT, 1e-9, 1, mode)
+        q, p = O.make_params(*args), F.make_params(*args)
+        assert q.dims() == dims == p.dims()
+        o = O.restatement()
+        f = O.alloc_fields(*dims, rng=np.random.default_rng(5))
+        init = {k[0].upper() + k[1:]: v.copy() for k, v in f.items()}
+        bad = []
+
+        def compare(ctx, what):
+            got = ctx.download({k: np.zeros_like(v) for k, v in init.items()})
+            k0, k1 = ctx.k0, ctx.k1
+            top = 1 if rank == world - 1 else 0
+            for name in ("Ez", "Hx", "Hy"):
+                if not np.array_equal(got[name][k0:k1].view(np.uint64), f[name.lower()][k0:k1].view(np.uint64)):
+                    bad.append((what, name))
+            for name in ("Ex", "Ey", "Hz"):
+                if not np.array_equal(got[name][k0:k1 + top].view(np.uint64),
+                                      f[name.lower()][k0:k1 + top].view(np.uint64)):
+                    bad.append((what, name))
+
+        with F.Context(p, device=rank, rank=rank, nranks=world) as ctx:
+            for k, v in variant.items():
+                ctx.set_option(k, v)
+            box = [F.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            ctx.comm_init(box[0])
+            ctx.upload(init)
+            # operator level, like the reference's loop body
+            t = 0.0
+            for _ in range(2):
+                if mode == 1:
+                    ctx.set_source(t); o.set_source(q, f, t)
+                ctx.update_H_field(); o.update_h(q, f)
+                if mode == 1:
+                    ctx.set_source(t); o.set_source(q, f, t)
+                ctx.update_E_field(); o.update_e(q, f)
+                t += DT
+            compare(ctx, "operators")
+            # fused / overlapped path
+            t2 = ctx.run(steps, t)
+            t3 = o.run(q, f, steps, t)
+            assert t2 == t3
+            compare(ctx, "run")
+            for v in range(6):
+                want = o.aggregate(q, f, v)[ctx.k0:ctx.k1]
+                if not np.array_equal(ctx.aggregate(v).view(np.uint64), want.view(np.uint64)):
+                    bad.append(("aggregate", v))
+            sums = ctx.checksum()
+        allsums = [None] * world
+        dist.all_gather_object(allsums, sums)
+        total = [sum(s[a] for s in allsums) % (1 << 64) for a in range(6)]
+        if total != F.checksum_host({k[0].upper() + k[1:]: v for k, v in f.items()}):
+            bad.append(("checksum", total))
+        ret[rank] = bad
+    finally:
+        dist.destroy_process_group()
+
+
+CASES = [((37, 28, 23), 1, 7, dict(kernel=1, strip=2, kchunk=8, warps_x=2, warps_y=2)),
+         ((37, 28, 23), 1, 5, dict(kernel=0)),
+         ((33, 40, 9), 0, 6, dict(kernel=1, strip=4, kchunk=3, warps_x=1, warps_y=4)),
+         ((70, 21, 8), 1, 6, dict(kernel=1, strip=1, kchunk=100, warps_x=4, warps_y=2)),
+         ((37, 28, 23), 1, 7, dict(kernel=2, strip=2, kchunk=8, warps_x=2, warps_y=2)),
+         ((33, 40, 9), 0, 6, dict(kernel=2, strip=3, kchunk=2, warps_x=1, warps_y=4)),
+         ((70, 21, 8), 1, 6, dict(kernel=2, strip=1, kchunk=100, warps_x=4, warps_y=1)),
+         ((40, 33, 4), 1, 5, dict(kernel=2, strip=4, kchunk=16, warps_x=1, warps_y=2))]
+
+
+@pytest.mark.parametrize("dims,mode,steps,variant", CASES)
+def test_slabs_match_single_domain(dims, mode, steps, variant):
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import torch.multiprocessing as mp
+    for world in sorted({2, min(ngpu, 4), min(ngpu, 8)}):
+        if world > dims[2]:
+            continue
+        ctx = mp.get_context("spawn")
+        ret = ctx.Manager().dict()
+        port = _free_port()
+        procs = [ctx.Process(target=_worker, args=(r, world, port, dims, mode, steps, variant, ret))
+                 for r in range(world)]
+        for pr in procs:
+            pr.start()
+        for pr in procs:
+            pr.join(timeout=300)
+            assert pr.exitcode == 0
+        assert dict(ret) == {r: [] for r in range(world)}, f"world={world}"

@@ -33,7 +33,14 @@ VARIANTS = [dict(kernel=0),
             dict(kernel=1, strip=2, kchunk=5, warps_x=1, warps_y=8),
             dict(kernel=1, strip=4, kchunk=32, warps_x=2, warps_y=4),
             dict(kernel=1, strip=4, kchunk=1, warps_x=8, warps_y=1),
-            dict(kernel=1, strip=2, kchunk=1000, warps_x=4, warps_y=2)]
+            dict(kernel=1, strip=2, kchunk=1000, warps_x=4, warps_y=2),
+            # fused single-sweep step (H and E in one launch, double-buffered state)
+            dict(kernel=2, strip=1, kchunk=32, warps_x=2, warps_y=2),
+            dict(kernel=2, strip=2, kchunk=2, warps_x=1, warps_y=4),
+            dict(kernel=2, strip=2, kchunk=7, warps_x=4, warps_y=1),
+            dict(kernel=2, strip=3, kchunk=5, warps_x=2, warps_y=2),
+            dict(kernel=2, strip=4, kchunk=1000, warps_x=1, warps_y=2),
+            dict(kernel=2, strip=2, kchunk=1, warps_x=2, warps_y=2)]
 GRIDS = [(0.037, 0.029, 0.023), (0.013, 0.011, 0.009), (0.05, 0.04, 0.03), (0.065, 0.033, 0.012),
          (0.034, 0.066, 0.007)]
 
@@ -55,7 +62,7 @@ def test_upload_download_roundtrip(F, oracle):
         assert ctx.checksum() == F.checksum_host(upper(f))
 
 
-@pytest.mark.parametrize("variant", VARIANTS[:4])
+@pytest.mark.parametrize("variant", VARIANTS[:4] + VARIANTS[7:8])
 @pytest.mark.parametrize("dims", GRIDS[:3])
 def test_operators_match_oracle(F, oracle, dims, variant):
     """update_H_field / update_E_field / set_source one call at a time (main.c:431, :469, :712)."""
@@ -127,7 +134,8 @@ def test_source_patch_must_fit(F):
 @pytest.mark.parametrize("name", ["stock_validation", "stock_computation", "ragged_50x39x29_computation",
                                   "random_37x28x23_computation", "random_33x17x9_validation",
                                   "cube128_computation_200"])
-def test_golden_runs(F, golden, tmp_path, name):
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_golden_runs(F, golden, tmp_path, name, kernel):
     """Whole runs against digests of the reference's own output (tests/golden/digests.json)."""
     g = golden[name]
     path = tmp_path / "p.txt"
@@ -135,6 +143,7 @@ def test_golden_runs(F, golden, tmp_path, name):
     p = F.load_parameters(path)
     assert list(p.dims()) == g["grid"]
     with F.Context(p) as ctx:
+        ctx.set_option("kernel", kernel)
         if g["init"].startswith("random:"):
             rng = np.random.default_rng(int(g["init"].split(":")[1]))
             f = {n: rng.uniform(-1.0, 1.0, size=s) for n, s in F.field_shapes(p).items()}
@@ -165,7 +174,8 @@ def test_golden_arrays_small_case(F, golden):
         assert_fields_equal(ctx.download(), {k: want[k] for k in want.files}, "golden arrays")
 
 
-def test_config2_cube256_1000_steps(F, golden, tmp_path):
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_config2_cube256_1000_steps(F, golden, tmp_path, kernel):
     """BASELINE.json configs[1]: 256^3, computation mode, 1000 steps, bit-exact vs the reference."""
     g = golden.get("cube256_computation_1000")
     if g is None:
@@ -175,6 +185,7 @@ def test_config2_cube256_1000_steps(F, golden, tmp_path):
     p = F.load_parameters(path)
     assert p.dims() == (256, 256, 256) and F.step_count(p) == 1000 == g["steps"]
     with F.Context(p) as ctx:
+        ctx.set_option("kernel", kernel)
         t = ctx.run(1000, 0.0)
         assert repr(t) == g["t_end"]
         out = ctx.download()
@@ -194,8 +205,9 @@ def test_aggregate_matches_oracle(F, oracle):
                 assert bits_equal(ctx.aggregate(v), o.aggregate(q, f, v)), v
 
 
+@pytest.mark.parametrize("kernel", [1, 2])
 @pytest.mark.parametrize("mode", [0, 1])
-def test_propagate_matches_reference_dumps(F, golden, tmp_path, mode):
+def test_propagate_matches_reference_dumps(F, golden, tmp_path, mode, kernel):
     """fdtd_propagate == propagate_fields (main.c:755-799): same dump files, same variables in the
     same order, same contents (validation mode adds aEy, aHx, aHz), same final state."""
     g = golden["propagate_tiny"][f"mode{mode}"]
@@ -204,6 +216,7 @@ def test_propagate_matches_reference_dumps(F, golden, tmp_path, mode):
     p = F.load_parameters(path)
     log = []
     with F.Context(p) as ctx:
+        ctx.set_option("kernel", kernel)
         if mode == 0:
             ctx.set_initial_conditions()
         steps, _ = ctx.propagate(

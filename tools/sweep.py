@@ -16,6 +16,8 @@ ap.add_argument("--n", type=int, default=1024)
 ap.add_argument("--nz", type=int, default=512)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--quick", action="store_true")
+ap.add_argument("--prefetch", action="store_true")
+ap.add_argument("--only", type=int, default=None, help="only this kernel id (plus the one-thread-per-cell reference)")
 args = ap.parse_args()
 
 p = F.make_params(args.n * 1e-3, args.n * 1e-3, args.nz * 1e-3, 1e-3, 6e-13, 1e-9, 1 << 30, 1)
@@ -27,6 +29,17 @@ for strip, kchunk, (wx, wy) in itertools.product((1, 2, 4), (8, 32, 128), shapes
     if args.quick and (kchunk != 32 or (wx, wy) not in ((2, 4), (4, 2))):
         continue
     variants.append(dict(kernel=1, strip=strip, kchunk=kchunk, warps_x=wx, warps_y=wy))
+
+for strip, kchunk, (wx, wy) in itertools.product((1, 2, 3, 4), (8, 32, 128), [(1, 4), (2, 2), (4, 1), (1, 2), (2, 1)]):
+    if args.quick and kchunk != 32:
+        continue
+    variants.append(dict(kernel=2, strip=strip, kchunk=kchunk, warps_x=wx, warps_y=wy))
+if args.prefetch:
+    variants = [dict(kernel=0)]
+    for strip, kchunk, pf, (wx, wy) in itertools.product((1, 2), (32, 128), (0, 1, 2, 3, 4, 6, 8), [(2, 2), (1, 4), (4, 1)]):
+        variants.append(dict(kernel=2, strip=strip, kchunk=kchunk, prefetch=pf, warps_x=wx, warps_y=wy))
+if args.only is not None:
+    variants = [v for v in variants if v["kernel"] == args.only or v["kernel"] == 0]
 
 ref_sum = None
 with F.Context(p) as ctx:
@@ -42,6 +55,6 @@ with F.Context(p) as ctx:
             ref_sum = s
         ok = s == ref_sum
         gcs = cells * args.steps / (total * 1e-3) / 1e9
-        hb = 72.0 * cells / (h / args.steps * 1e-3) / 1e9
-        eb = 72.0 * cells / (e / args.steps * 1e-3) / 1e9
+        hb = 72.0 * cells / (max(h, 1e-6) / args.steps * 1e-3) / 1e9
+        eb = 72.0 * cells / (max(e, 1e-6) / args.steps * 1e-3) / 1e9
         print(json.dumps(dict(v, gcell_s=round(gcs, 2), h_gbs=round(hb), e_gbs=round(eb), same_bits=ok)), flush=True)
