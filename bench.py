@@ -144,7 +144,7 @@ def workload_config(n_gpus):
                         f"dx=1mm dt=0.6ps, double precision (BASELINE.json configs[2]: 1024^3 per GPU)",
             "cells": N_XY * N_XY * NZ_PER_GPU * n_gpus,
             "decomposition": f"{n_gpus} z-slab(s) of {NZ_PER_GPU} planes, one process per GPU",
-            "l2": "state is 51.6 GB per GPU, far larger than the 126 MB L2; no flush needed"}
+            "l2": "state is 51.6 GB per GPU (held twice by the fused step), far larger than the 126 MB L2; no flush needed"}
 
 
 def run_reference_arm(args):
@@ -244,16 +244,35 @@ def main():
 
     # ---- roofline of the dominant kernel -----------------------------------------------------
     peak, peak_src = peak_hbm()
-    dom_ms = max(h_ms, e_ms) / K
-    dom_name = "k_update_h_march (H half-step)" if h_ms >= e_ms else "k_update_e_march (E half-step)"
-    alg_bytes = BYTES_PER_CELL_HALF_STEP * cells_local
+    kernel_id = ctx.get_option("kernel")
+    if kernel_id >= 2:
+        # fused step: ONE launch advances every cell by a full time step (H and E)
+        dom_ms = h_ms / K
+        dom_name = "k_step_fused_tma (H+E in one sweep, TMA-staged)" if kernel_id == 3 else "k_step_fused (H+E in one sweep)"
+        alg_bytes = 2 * BYTES_PER_CELL_HALF_STEP * cells_local   # 144 B per cell-update
+        min_bytes = 96.0 * cells_local                           # what a fused sweep has to move: 6 reads + 6 writes
+        traffic = TRAFFIC_FUSED_BYTES_PER_CELL * cells_local if TRAFFIC_FUSED_BYTES_PER_CELL else None
+        traffic_src = TRAFFIC_FUSED_SOURCE
+    else:
+        dom_ms = max(h_ms, e_ms) / K
+        dom_name = "k_update_h_march (H half-step)" if h_ms >= e_ms else "k_update_e_march (E half-step)"
+        alg_bytes = BYTES_PER_CELL_HALF_STEP * cells_local
+        min_bytes = alg_bytes
+        traffic = TRAFFIC_BYTES_PER_CELL_HALF_STEP * cells_local
+        traffic_src = TRAFFIC_SOURCE
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": TRAFFIC_BYTES_PER_CELL_HALF_STEP * cells_local,
-                "traffic_source": TRAFFIC_SOURCE,
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": dom_ms,
-                "h_ms_per_step": h_ms / K, "e_ms_per_step": e_ms / K,
-                "step_frac_of_roofline": (2 * alg_bytes / (total_ms / K * 1e-3) / 1e9) / peak}
+                "bytes_per_cell_update_basis": 144,
+                "fused_minimum_bytes_per_launch": min_bytes,
+                "achieved_on_fused_minimum": min_bytes / (dom_ms * 1e-3) / 1e9,
+                "frac_on_fused_minimum": min_bytes / (dom_ms * 1e-3) / 1e9 / peak,
+                "note": ("achieved/frac use SURVEY.md 8(d)'s 144 B per cell-update (the split H + E half-steps); "
+                         "the fused sweep reads and writes each of the six arrays once per step = 96 B per "
+                         "cell-update, so frac can exceed 1: frac_on_fused_minimum is the honest HBM utilisation"
+                         if kernel_id >= 2 else "two launches per step; 72 B per cell and half-step"),
+                "step_frac_of_roofline": (2 * BYTES_PER_CELL_HALF_STEP * cells_local / (total_ms / K * 1e-3) / 1e9) / peak}
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------
     e2e = None
@@ -295,7 +314,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic (hash-pattern fields in HBM, waveguide source on)",
                 "config": dict(workload_config(world),
-                               kernel={k: ctx.get_option(k) for k in ("kernel", "strip", "kchunk", "warps_x", "warps_y")}),
+                               kernel={k: ctx.get_option(k) for k in ("kernel", "strip", "kchunk", "warps_x", "warps_y", "stages")}),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
                 "clocks": clocks.summary(), "hbm_bytes_per_gpu": ctx.info()["hbm_bytes"]}
         print(json.dumps(line), flush=True)
@@ -309,6 +328,10 @@ def main():
 # save/restore of the state stays small; per-cell traffic does not depend on the plane count)
 TRAFFIC_BYTES_PER_CELL_HALF_STEP = 20.022561e9 / (1024 * 1024 * 256)
 TRAFFIC_SOURCE = "profiles/r01_split_ncu_full_raw.csv (k_update_h_march<2>, 20.02 GB per launch at 1024x1024x256)"
+# same for the fused TMA step (None until captured)
+TRAFFIC_FUSED_BYTES_PER_CELL = (14.598498e9 + 12.923797e9) / (1024 * 1024 * 256)
+TRAFFIC_FUSED_SOURCE = ("profiles/r01_tma_ncu_full_raw.csv (k_step_fused_tma<2>, 14.60 GB read + 12.92 GB written "
+                        "per launch at 1024x1024x256; the fused sweep's minimum is 96 B x cells = 25.77 GB)")
 
 if __name__ == "__main__":
     main()

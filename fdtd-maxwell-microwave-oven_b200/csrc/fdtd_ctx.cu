@@ -9,6 +9,7 @@
 #include "fdtd_internal.h"
 #include "fdtd_kernels.cuh"
 #include "fdtd_fused.cuh"
+#include "fdtd_fused_tma.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -133,8 +134,15 @@ struct fdtd_ctx {
     double *src_one_dev; /* single row for the operator-level fdtd_set_source */
 
     /* options */
-    long opt_kernel, opt_strip, opt_kchunk, opt_wx, opt_wy, opt_prefetch;
+    long opt_kernel, opt_strip, opt_kchunk, opt_wx, opt_wy, opt_prefetch, opt_stages;
+
+    /* tensor maps of the TMA-staged fused step: [buffer set][array], valid for tma_bx x tma_by tiles */
+    TmaMaps tma_maps[2];
+    double *tma_base[2];
+    int tma_bx, tma_by;
     mutable long launches; /* kernels of this library launched so far (reports) */
+    int launch_error;      /* first failure inside a launch helper, reported by queue_step */
+    bool kernel_auto;      /* "kernel" was not chosen by the caller: may fall back to the split kernels */
 
     /* dump scratch for fdtd_aggregate */
     double *agg_dev;
@@ -371,11 +379,95 @@ void launch_fused_t(const fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, c
     ++c->launches;
 }
 
+/* cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda) */
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+int encode_maps(fdtd_ctx *c, int bx, int by)
+{
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) {
+            fdtd_set_error("cuTensorMapEncodeTiled is not available in this driver");
+            return FDTD_E_CUDA;
+        }
+        encode = (EncodeTiledFn)fn;
+    }
+    double *sets[2] = {c->base, c->base2};
+    if (c->tma_bx == bx && c->tma_by == by && c->tma_base[0] == sets[0] && c->tma_base[1] == sets[1])
+        return FDTD_OK;
+    if (c->tma_bx == bx && c->tma_by == by && c->tma_base[0] == sets[1] && c->tma_base[1] == sets[0]) {
+        std::swap(c->tma_maps[0], c->tma_maps[1]); /* the two states swapped roles */
+        std::swap(c->tma_base[0], c->tma_base[1]);
+        return FDTD_OK;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)c->g.P, (cuuint64_t)c->g.R, (cuuint64_t)c->g.planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)c->g.P * 8, (cuuint64_t)c->g.PR * 8};
+    const cuuint32_t box[3] = {(cuuint32_t)(bx + 4), (cuuint32_t)(by + 2), 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    for (int set = 0; set < 2; ++set)
+        for (int a = 0; a < 6; ++a) {
+            CUresult r = encode(&c->tma_maps[set].m[a], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
+                                sets[set] + (size_t)a * c->array_elems, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                fdtd_set_error("cuTensorMapEncodeTiled failed with CUresult %d (box %d x %d)", (int)r, bx + 2, by + 2);
+                return FDTD_E_CUDA;
+            }
+        }
+    c->tma_bx = bx;
+    c->tma_by = by;
+    c->tma_base[0] = sets[0];
+    c->tma_base[1] = sets[1];
+    return FDTD_OK;
+}
+
+template <int TY>
+int launch_fused_tma_t(fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStream_t st)
+{
+    const int wx = (int)c->opt_wx, wy = (int)c->opt_wy;
+    const int bx = 32 * wx, by = wy * TY;
+    FDTD_TRY(encode_maps(c, bx, by));
+    const int stages = (int)c->opt_stages;
+    const size_t smem = (size_t)stages * 6 * tma_box_doubles(bx, by) * sizeof(double);
+    static size_t configured = 0;
+    if (smem > configured) {
+        CUDA_TRY(cudaFuncSetAttribute(k_step_fused_tma<TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+        configured = 227 * 1024;
+    }
+    if (smem > 226 * 1024) {
+        fdtd_set_error("TMA ring of %d stages x %d x %d tile needs %zu bytes of shared memory", stages, bx, by, smem);
+        return FDTD_E_ARG;
+    }
+    Span sp{kl_begin, kl_end, (int)std::max(c->opt_kchunk, 2L), 0};
+    dim3 block(bx, wy);
+    dim3 grid((c->g.I + 1 + bx - 1) / bx, (c->g.J + 1 + by - 1) / by, (kl_end - kl_begin + sp.kchunk - 1) / sp.kchunk);
+    k_step_fused_tma<TY><<<grid, block, smem, st>>>(c->g, c->tma_maps[0], c->f2, c->ch, c->ce, s, sp, stages);
+    ++c->launches;
+    return FDTD_OK;
+}
+
 /* one whole step (H then E) of the local planes [kl_begin, kl_end): reads c->f, writes c->f2 */
-void launch_fused(const fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStream_t st)
+void launch_fused(fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStream_t st)
 {
     if (kl_end <= kl_begin)
         return;
+    if (c->opt_kernel == 3) {
+        int rc;
+        switch (c->opt_strip) {
+        case 1: rc = launch_fused_tma_t<1>(c, s, kl_begin, kl_end, st); break;
+        default: rc = launch_fused_tma_t<2>(c, s, kl_begin, kl_end, st); break;
+        }
+        if (rc != FDTD_OK)
+            c->launch_error = rc;
+        return;
+    }
     switch (c->opt_strip) {
     case 1: launch_fused_t<1>(c, s, kl_begin, kl_end, st); break;
     case 3: launch_fused_t<3>(c, s, kl_begin, kl_end, st); break;
@@ -455,7 +547,7 @@ int refresh_halos(fdtd_ctx *c)
 {
     if (c->nranks == 1)
         return FDTD_OK;
-    const bool fused = c->opt_kernel == 2;
+    const bool fused = c->opt_kernel >= 2;
     if (!c->e_halo_valid) {
         FDTD_TRY(exchange_e(c, c->s_main, false));
         c->e_halo_valid = true;
@@ -478,7 +570,7 @@ int queue_step(fdtd_ctx *c, const Src &s, cudaEvent_t ev_h_begin, cudaEvent_t ev
     if (ev_h_begin)
         CUDA_TRY(cudaEventRecord(ev_h_begin, c->s_main));
 
-    if (c->opt_kernel == 2) {
+    if (c->opt_kernel >= 2) {
         /* fused: one sweep does H and E; reads c->f, writes c->f2, then the two swap */
         if (c->nranks == 1) {
             launch_fused(c, s, 1, h_end, c->s_main);
@@ -515,6 +607,11 @@ int queue_step(fdtd_ctx *c, const Src &s, cudaEvent_t ev_h_begin, cudaEvent_t ev
             CUDA_TRY(cudaEventRecord(ev_mid, c->s_main));
         if (ev_e_end)
             CUDA_TRY(cudaEventRecord(ev_e_end, c->s_main));
+        if (c->launch_error != FDTD_OK) {
+            const int rc = c->launch_error;
+            c->launch_error = FDTD_OK;
+            return rc;
+        }
         CUDA_TRY(cudaGetLastError());
         return FDTD_OK;
     }
@@ -590,8 +687,21 @@ int stage_source_rows(fdtd_ctx *c, size_t count, double *t_io)
 int run_impl(fdtd_ctx *c, size_t steps, double *time_counter, float *total_ms, float *h_ms, float *e_ms)
 {
     FDTD_TRY(use_device(c));
-    if (c->opt_kernel == 2)
-        FDTD_TRY(ensure_pong(c));
+    if (c->opt_kernel >= 2) {
+        int rc = ensure_pong(c);
+        if (rc == FDTD_E_NOMEM && c->kernel_auto) {
+            /* the fused step needs the state twice in HBM; when that does not fit, the in-place
+             * split kernels (144 B per cell-update instead of 96) take over -- still on the GPU */
+            cudaGetLastError();
+            c->opt_kernel = 1;
+            c->opt_strip = 2;
+            c->opt_kchunk = 8;
+            c->opt_wx = 2;
+            c->opt_wy = 2;
+        } else if (rc != FDTD_OK) {
+            return rc;
+        }
+    }
     FDTD_TRY(refresh_halos(c));
     if (c->nranks > 1) {
         /* the first step's waits need recorded events */
@@ -721,11 +831,16 @@ int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx
     c->array_elems = (size_t)g.PR * (size_t)g.planes;
     c->ch = fdtd_factor_h(p);
     c->ce = fdtd_factor_e(p);
-    c->opt_kernel = 1;
+    /* default: the TMA-staged fused step with the launch shape that won the sweep on a B200
+     * (profiles/): 128 x 4 tile, 2 rows per thread, 32 planes per block, 3 stages in flight */
+    c->opt_kernel = 3;
+    c->kernel_auto = true;
     c->opt_strip = 2;
-    c->opt_kchunk = 8;
-    c->opt_wx = 2;
+    c->opt_kchunk = 32;
+    c->opt_wx = 4;
     c->opt_wy = 2;
+    c->opt_stages = 3;
+    c->opt_prefetch = 3;
 
     rc = fdtd_source_plan_make(p, &c->plan);
     if (rc != FDTD_OK) {
@@ -880,7 +995,11 @@ int fdtd_ctx_set_option(fdtd_ctx *c, const char *key, long value)
         fdtd_set_error("fdtd_ctx_set_option: NULL key");
         return FDTD_E_ARG;
     }
-    if (!strcmp(key, "kernel") && value >= 0 && value <= 2) c->opt_kernel = value;
+    if (!strcmp(key, "kernel") && value >= 0 && value <= 3) {
+        c->opt_kernel = value;
+        c->kernel_auto = false;
+    }
+    else if (!strcmp(key, "stages") && value >= 2 && value <= kTmaMaxStages) c->opt_stages = value;
     else if (!strcmp(key, "strip") && value >= 1 && value <= 4) c->opt_strip = value;
     else if (!strcmp(key, "kchunk") && value >= 1 && value <= 1 << 20) c->opt_kchunk = value;
     else if (!strcmp(key, "warps_x") && value >= 1 && value <= 8) c->opt_wx = value;
@@ -906,6 +1025,7 @@ int fdtd_ctx_get_option(fdtd_ctx *c, const char *key, long *value)
     else if (!strcmp(key, "warps_x")) *value = c->opt_wx;
     else if (!strcmp(key, "warps_y")) *value = c->opt_wy;
     else if (!strcmp(key, "prefetch")) *value = c->opt_prefetch;
+    else if (!strcmp(key, "stages")) *value = c->opt_stages;
     else if (!strcmp(key, "k0")) *value = (long)c->k0;
     else if (!strcmp(key, "k1")) *value = (long)c->k1;
     else if (!strcmp(key, "launches")) *value = c->launches;

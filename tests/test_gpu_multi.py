@@ -96,7 +96,9 @@ CASES = [((37, 28, 23), 1, 7, dict(kernel=1, strip=2, kchunk=8, warps_x=2, warps
          ((37, 28, 23), 1, 7, dict(kernel=2, strip=2, kchunk=8, warps_x=2, warps_y=2)),
          ((33, 40, 9), 0, 6, dict(kernel=2, strip=3, kchunk=2, warps_x=1, warps_y=4)),
          ((70, 21, 8), 1, 6, dict(kernel=2, strip=1, kchunk=100, warps_x=4, warps_y=1)),
-         ((40, 33, 4), 1, 5, dict(kernel=2, strip=4, kchunk=16, warps_x=1, warps_y=2))]
+         ((40, 33, 4), 1, 5, dict(kernel=2, strip=4, kchunk=16, warps_x=1, warps_y=2)),
+         ((37, 28, 23), 1, 7, dict(kernel=3, strip=2, kchunk=8, warps_x=2, warps_y=2, stages=3)),
+         ((70, 21, 8), 0, 6, dict(kernel=3, strip=1, kchunk=100, warps_x=1, warps_y=4, stages=4))]
 
 
 @pytest.mark.parametrize("dims,mode,steps,variant", CASES)

@@ -40,7 +40,12 @@ VARIANTS = [dict(kernel=0),
             dict(kernel=2, strip=2, kchunk=7, warps_x=4, warps_y=1),
             dict(kernel=2, strip=3, kchunk=5, warps_x=2, warps_y=2),
             dict(kernel=2, strip=4, kchunk=1000, warps_x=1, warps_y=2),
-            dict(kernel=2, strip=2, kchunk=1, warps_x=2, warps_y=2)]
+            dict(kernel=2, strip=2, kchunk=1, warps_x=2, warps_y=2),
+            # the same fused step with TMA-staged operands (cp.async.bulk.tensor + mbarrier ring)
+            dict(kernel=3, strip=1, kchunk=32, warps_x=1, warps_y=4, stages=3),
+            dict(kernel=3, strip=2, kchunk=5, warps_x=2, warps_y=2, stages=2),
+            dict(kernel=3, strip=2, kchunk=1000, warps_x=1, warps_y=8, stages=4),
+            dict(kernel=3, strip=1, kchunk=2, warps_x=2, warps_y=4, stages=8)]
 GRIDS = [(0.037, 0.029, 0.023), (0.013, 0.011, 0.009), (0.05, 0.04, 0.03), (0.065, 0.033, 0.012),
          (0.034, 0.066, 0.007)]
 
@@ -134,7 +139,7 @@ def test_source_patch_must_fit(F):
 @pytest.mark.parametrize("name", ["stock_validation", "stock_computation", "ragged_50x39x29_computation",
                                   "random_37x28x23_computation", "random_33x17x9_validation",
                                   "cube128_computation_200"])
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
 def test_golden_runs(F, golden, tmp_path, name, kernel):
     """Whole runs against digests of the reference's own output (tests/golden/digests.json)."""
     g = golden[name]
@@ -174,7 +179,7 @@ def test_golden_arrays_small_case(F, golden):
         assert_fields_equal(ctx.download(), {k: want[k] for k in want.files}, "golden arrays")
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
 def test_config2_cube256_1000_steps(F, golden, tmp_path, kernel):
     """BASELINE.json configs[1]: 256^3, computation mode, 1000 steps, bit-exact vs the reference."""
     g = golden.get("cube256_computation_1000")
@@ -205,7 +210,7 @@ def test_aggregate_matches_oracle(F, oracle):
                 assert bits_equal(ctx.aggregate(v), o.aggregate(q, f, v)), v
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
 @pytest.mark.parametrize("mode", [0, 1])
 def test_propagate_matches_reference_dumps(F, golden, tmp_path, mode, kernel):
     """fdtd_propagate == propagate_fields (main.c:755-799): same dump files, same variables in the

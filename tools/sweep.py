@@ -16,6 +16,7 @@ ap.add_argument("--n", type=int, default=1024)
 ap.add_argument("--nz", type=int, default=512)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--quick", action="store_true")
+ap.add_argument("--tma", action="store_true")
 ap.add_argument("--prefetch", action="store_true")
 ap.add_argument("--only", type=int, default=None, help="only this kernel id (plus the one-thread-per-cell reference)")
 args = ap.parse_args()
@@ -38,6 +39,10 @@ if args.prefetch:
     variants = [dict(kernel=0)]
     for strip, kchunk, pf, (wx, wy) in itertools.product((1, 2), (32, 128), (0, 1, 2, 3, 4, 6, 8), [(2, 2), (1, 4), (4, 1)]):
         variants.append(dict(kernel=2, strip=strip, kchunk=kchunk, prefetch=pf, warps_x=wx, warps_y=wy))
+if args.tma:
+    variants = [dict(kernel=0), dict(kernel=2, strip=1, kchunk=32, prefetch=3, warps_x=1, warps_y=4)]
+    for strip, kchunk, stages, (wx, wy) in itertools.product((1, 2), (32, 128), (2, 3, 4, 6), [(1, 4), (1, 8), (2, 4), (2, 2), (4, 2), (4, 1), (8, 1)]):
+        variants.append(dict(kernel=3, strip=strip, kchunk=kchunk, stages=stages, warps_x=wx, warps_y=wy))
 if args.only is not None:
     variants = [v for v in variants if v["kernel"] == args.only or v["kernel"] == 0]
 
@@ -46,6 +51,11 @@ with F.Context(p) as ctx:
     for v in variants:
         for k, val in v.items():
             ctx.set_option(k, val)
+        try:
+            ctx.run(1, 0.0)
+        except F.FdtdError as e:
+            print(json.dumps(dict(v, error=str(e))), flush=True)
+            continue
         ctx.fill_test_pattern(1)
         t = ctx.run(2, 0.0)
         ctx.sync()
