@@ -98,6 +98,8 @@ SIGNATURES = {
     "fdtd_sync": (C.c_int, [_CTX]),
     "fdtd_aggregate": (C.c_int, [_CTX, C.c_int, _D]),
     "fdtd_propagate": (C.c_int, [_CTX, C.POINTER(DumpSink), C.POINTER(C.c_size_t), _D]),
+    "fdtd_energy": (C.c_int, [_CTX, C.c_int, _D, _D]),
+    "fdtd_validation_error": (C.c_int, [_CTX, C.c_double, _D, _D]),
     "fdtd_fill_test_pattern": (C.c_int, [_CTX, C.c_ulonglong]),
     "fdtd_checksum": (C.c_int, [_CTX, C.POINTER(C.c_ulonglong)]),
     "fdtd_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -334,6 +336,16 @@ class Context:
         out = np.empty((self.k1 - self.k0, ny, nx))
         _check(lib.fdtd_aggregate(self._h, int(var), out.ctypes.data_as(_D)))
         return out
+
+    def energy(self, as_coded=False):
+        e, h = C.c_double(), C.c_double()
+        _check(lib.fdtd_energy(self._h, 1 if as_coded else 0, C.byref(e), C.byref(h)))
+        return e.value, h.value
+
+    def validation_error(self, t):
+        sums, rel = (C.c_double * 6)(), (C.c_double * 3)()
+        _check(lib.fdtd_validation_error(self._h, float(t), sums, rel))
+        return list(sums), list(rel)
 
     def fill_test_pattern(self, seed):
         _check(lib.fdtd_fill_test_pattern(self._h, int(seed)))

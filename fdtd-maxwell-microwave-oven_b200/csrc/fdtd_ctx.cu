@@ -16,6 +16,7 @@
 #include <pthread.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1494,6 +1495,83 @@ int fdtd_propagate(fdtd_ctx *c, const fdtd_dump_sink *sink, size_t *steps_done, 
     if (steps_done) *steps_done = steps;
     if (time_counter) *time_counter = t;
     return rc;
+}
+
+int fdtd_energy(fdtd_ctx *c, int as_coded, double *e_energy, double *h_energy)
+{
+    FDTD_TRY(check_ctx(c, "fdtd_energy"));
+    FDTD_TRY(use_device(c));
+    if (c->nranks > 1) { /* the top zone plane averages with node plane k1 of Ex, Ey, Hz */
+        FDTD_TRY(exchange_e(c, c->s_main, true));
+        c->e_halo_valid = true;
+    }
+    double *dev = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&dev, 6 * sizeof(double)));
+    cudaMemsetAsync(dev, 0, 6 * sizeof(double), c->s_main);
+    dim3 block(64, 4);
+    dim3 grid((c->g.I + 63) / 64, (c->g.J + 3) / 4, c->g.nk);
+    k_energy<<<grid, block, 0, c->s_main>>>(c->g, c->f, as_coded, dev);
+    double s[6];
+    cudaError_t e = cudaMemcpyAsync(s, dev, sizeof s, cudaMemcpyDeviceToHost, c->s_main);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(c->s_main);
+    cudaFree(dev);
+    if (e != cudaSuccess) {
+        fdtd_set_error("fdtd_energy: %s", cudaGetErrorString(e));
+        return FDTD_E_CUDA;
+    }
+    const double dv = pow(c->p.spatial_step, 3); /* main.c:613 */
+    if (e_energy) *e_energy = (s[0] * dv + s[1] * dv + s[2] * dv) * FDTD_EPSILON / 2.; /* main.c:631 */
+    if (h_energy) *h_energy = (s[3] * dv + s[4] * dv + s[5] * dv) * FDTD_MU / 2.;      /* main.c:665 */
+    return FDTD_OK;
+}
+
+int fdtd_validation_error(fdtd_ctx *c, double t, double sums[6], double rel_l2[3])
+{
+    FDTD_TRY(check_ctx(c, "fdtd_validation_error"));
+    FDTD_TRY(use_device(c));
+    const fdtd_params &p = c->p;
+    const size_t nk = p.maxk + 2, ni = p.maxi + 2;
+    std::vector<double> tab(2 * nk + 2 * ni);
+    double *sk = tab.data(), *ck = sk + nk, *si = ck + nk, *ci = si + ni;
+    for (size_t k = 0; k < p.maxk + 1; ++k) {
+        sk[k] = sin(FDTD_PI * k * p.spatial_step / p.height);
+        ck[k] = cos(FDTD_PI * k * p.spatial_step / p.height);
+    }
+    for (size_t i = 0; i < p.maxi + 1; ++i) {
+        si[i] = sin(FDTD_PI * i * p.spatial_step / p.length);
+        ci[i] = cos(FDTD_PI * i * p.spatial_step / p.length);
+    }
+    /* main.c:672-675 */
+    const double f_mnl = 0.5 * FDTD_CELERITY * sqrt(pow(FDTD_PI / p.height, 2) + pow(FDTD_PI / p.length, 2)) / FDTD_PI;
+    const double omega = 2.0 * FDTD_PI * f_mnl;
+    const double z_te = (omega * FDTD_MU) / sqrt(pow(omega, 2) * FDTD_MU * FDTD_EPSILON - pow(FDTD_PI / p.length, 2));
+    const double a_ey = cos(2 * FDTD_PI * f_mnl * t);
+    const double a_hx = (1.0 / z_te) * sin(2 * FDTD_PI * f_mnl * t);
+    const double a_hz = -FDTD_PI / (omega * FDTD_MU * p.length) * sin(2 * FDTD_PI * f_mnl * t);
+    double *dev = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&dev, (tab.size() + 6) * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(dev + 6, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, c->s_main);
+    cudaMemsetAsync(dev, 0, 6 * sizeof(double), c->s_main);
+    dim3 block(64, 4);
+    dim3 grid((c->g.I + 1 + 63) / 64, (c->g.J + 3) / 4, c->g.nk + c->g.top);
+    k_validation_error<<<grid, block, 0, c->s_main>>>(c->g, c->f, dev + 6, dev + 6 + nk, dev + 6 + 2 * nk,
+                                                     dev + 6 + 2 * nk + ni, a_ey, a_hx, a_hz, c->g.top, dev);
+    double s[6];
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(s, dev, sizeof s, cudaMemcpyDeviceToHost, c->s_main);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(c->s_main);
+    cudaFree(dev);
+    if (e != cudaSuccess) {
+        fdtd_set_error("fdtd_validation_error: %s", cudaGetErrorString(e));
+        return FDTD_E_CUDA;
+    }
+    for (int v = 0; v < 6; ++v)
+        if (sums) sums[v] = s[v];
+    for (int v = 0; v < 3; ++v)
+        if (rel_l2) rel_l2[v] = s[2 * v + 1] > 0.0 ? sqrt(s[2 * v] / s[2 * v + 1]) : 0.0;
+    return FDTD_OK;
 }
 
 static DenseView dense_view(const fdtd_ctx *c, int idx)

@@ -175,6 +175,18 @@ int fdtd_propagate(fdtd_ctx *ctx, const fdtd_dump_sink *sink, size_t *steps_done
 int fdtd_host_alloc(size_t bytes, void **out);
 int fdtd_host_free(void *ptr);
 
+/* Diagnostics that sit next to the path in the reference (they never feed back into the fields).
+ * Both are reductions and agree with the reference's sequential sums to rounding, not bit for bit.
+ * A slab context returns its own zones' contribution; add the slabs up for the cavity.
+ *
+ * fdtd_energy: calculate_E_energy() / calculate_H_energy(), main.c:602-668.  as_coded != 0 keeps the
+ *   reference's indexing of Ez with Hz's strides (main.c:627); 0 uses the intended zone average.
+ * fdtd_validation_error: against the analytic TE101 fields of update_validation_fields_then_subfdtd(),
+ *   main.c:670-710, at time_counter: sums[] = {sum (a-Ey)^2, sum a^2, same for Hx, same for Hz};
+ *   rel_l2[] = sqrt(num/den) per field (the report's e_r, description.pdf eq. 2).  Either may be NULL. */
+int fdtd_energy(fdtd_ctx *ctx, int as_coded, double *e_energy, double *h_energy);
+int fdtd_validation_error(fdtd_ctx *ctx, double time_counter, double sums[6], double rel_l2[3]);
+
 /* Full-size test support (no host copy of a 1024^3 state exists).  Both are pure functions of an
  * element's index in the reference's dense arrays (main.c:379-407), independent of pitch and slabs.
  * fdtd_fill_test_pattern: every element of the six arrays := 2u-1 with u = (splitmix64(seed ^

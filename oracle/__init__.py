@@ -75,7 +75,8 @@ class Checker:
                "set_source": (None, [P, F, C.c_double]),
                "run": (None, [P, F, C.c_size_t, D]),
                "aggregate": (None, [P, F, C.c_int, D]),
-               "validation_fields": (None, [P, F, D, D, D, C.c_double])}
+               "validation_fields": (None, [P, F, D, D, D, C.c_double]),
+               "energy": (None, [P, F, D])}
         if prefix == "oracle_":
             sig.update({"make_params": (None, [C.c_float, C.c_float, C.c_float, C.c_double, C.c_double,
                                                C.c_float, C.c_uint, C.c_int, P]),
@@ -129,6 +130,12 @@ class Checker:
         self._validation_fields(C.byref(p), C.byref(_ptrs(fields)), v["ey"].ctypes.data_as(D),
                                 v["hx"].ctypes.data_as(D), v["hz"].ctypes.data_as(D), float(t))
         return v
+
+    def energy(self, p, fields):
+        """(electric, magnetic) energy as coded at main.c:602-668"""
+        out = (C.c_double * 2)()
+        self._energy(C.byref(p), C.byref(_ptrs(fields)), out)
+        return out[0], out[1]
 
     def propagate(self, p, fields, on_var):
         """reference only: run propagate_fields (main.c:755-799); on_var(kind, name, array|None)."""

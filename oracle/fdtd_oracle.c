@@ -328,3 +328,31 @@ void oracle_validation_fields(const oracle_params *p, const oracle_fields *f,
                           sin(ORACLE_PI * i * dx / p->length)) - f->hz[n];
             }
 }
+
+/* main.c:602-668, as coded: the Ez average at main.c:627 indexes Ez with Hz's strides (kHz).
+ * out[0] = electric, out[1] = magnetic energy. */
+void oracle_energy(const oracle_params *p, const oracle_fields *f, double out[2])
+{
+    const shape sex = shape_ex(p), sey = shape_ey(p), shx = shape_hx(p), shy = shape_hy(p), shz = shape_hz(p);
+    const double dv = pow(p->spatial_step, 3);
+    double ex = 0.0, ey = 0.0, ez = 0.0, hx = 0.0, hy = 0.0, hz = 0.0;
+    for (size_t k = 0; k < p->nz; k++)
+        for (size_t j = 0; j < p->ny; j++)
+            for (size_t i = 0; i < p->nx; i++) {
+                const size_t oex = i + j * sex.row + k * sex.plane, oey = i + j * sey.row + k * sey.plane;
+                const size_t ohz = i + j * shz.row + k * shz.plane; /* used for Ez too, main.c:627 */
+                const double mex = (f->ex[oex] + f->ex[oex + sex.plane] + f->ex[oex + sex.row] +
+                                    f->ex[oex + sex.row + sex.plane]) / 4.;
+                const double mey = (f->ey[oey] + f->ey[oey + 1] + f->ey[oey + sey.plane] +
+                                    f->ey[oey + 1 + sey.plane]) / 4.;
+                const double mez = (f->ez[ohz] + f->ez[ohz + shz.row] + f->ez[ohz + 1] + f->ez[ohz + 1 + shz.row]) / 4.;
+                const size_t ohx = i + j * shx.row + k * shx.plane, ohy = i + j * shy.row + k * shy.plane;
+                const double mhx = (f->hx[ohx] + f->hx[ohx + 1]) / 2.;
+                const double mhy = (f->hy[ohy] + f->hy[ohy + shy.row]) / 2.;
+                const double mhz = (f->hz[ohz] + f->hz[ohz + shz.plane]) / 2.;
+                ex += pow(mex, 2) * dv; ey += pow(mey, 2) * dv; ez += pow(mez, 2) * dv;
+                hx += pow(mhx, 2) * dv; hy += pow(mhy, 2) * dv; hz += pow(mhz, 2) * dv;
+            }
+    out[0] = (ex + ey + ez) * ORACLE_EPSILON / 2.;
+    out[1] = (hx + hy + hz) * ORACLE_MU / 2.;
+}

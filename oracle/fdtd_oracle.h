@@ -77,6 +77,9 @@ void oracle_aggregate(const oracle_params *p, const oracle_fields *f, int var, d
 void oracle_validation_fields(const oracle_params *p, const oracle_fields *f,
                               double *vey, double *vhx, double *vhz, double t);
 
+/* main.c:602-668 as coded (Ez indexed with Hz's strides, main.c:627): out = {electric, magnetic} */
+void oracle_energy(const oracle_params *p, const oracle_fields *f, double out[2]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -142,6 +142,14 @@ void ref_validation_fields(const oracle_params *q, const oracle_fields *g,
     update_validation_fields_then_subfdtd(&p, &f, &v, t);
 }
 
+void ref_energy(const oracle_params *q, const oracle_fields *g, double out[2])
+{
+    Parameters p = to_ref(q);
+    Fields f = to_ref_fields(g);
+    out[0] = calculate_E_energy(&f, &p);
+    out[1] = calculate_H_energy(&f, &p);
+}
+
 /* The reference's whole stepping loop, propagate_fields (main.c:755-799), on caller-owned
  * arrays.  Every variable the reference hands to Silo is passed to `rec` (see silo_stub). */
 void ref_propagate(const oracle_params *q, const oracle_fields *g, silo_stub_recorder rec)

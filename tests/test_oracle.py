@@ -151,3 +151,13 @@ def test_reference_propagate_matches_golden(oracle, golden, tmp_path):
         r.propagate(p, f, on_var)
         assert log == g["dumps"]
         assert {k: digest(v) for k, v in f.items()} == g["final_sha256"]
+
+
+@needs_ref
+def test_energy_restatement_matches_reference(oracle):
+    """calculate_E_energy / calculate_H_energy (main.c:602-668) incl. the Ez[kHz] slip at main.c:627."""
+    o, r = oracle.restatement(), oracle.reference()
+    for dims in ((0.013, 0.011, 0.009), (0.021, 0.016, 0.012)):
+        p = oracle.make_params(*dims, 0.001, 6e-13, 1.2e-10, 2, 1)
+        f = oracle.alloc_fields(*p.dims(), rng=np.random.default_rng(3))
+        assert o.energy(p, f) == r.energy(p, f)
