@@ -1248,6 +1248,7 @@ struct DumpPipe {
     pthread_cond_t cv;
     int pending_iteration;      /* -1: none */
     bool scratch_busy;          /* dev[] still being drained */
+    bool writer_busy;           /* a dump is between sink.begin and sink.end */
     bool stop;
     int error;                  /* first sink / CUDA failure seen by the writer */
     char error_msg[256];
@@ -1268,6 +1269,7 @@ void *writer_main(void *arg)
         }
         const int iteration = dp->pending_iteration;
         dp->pending_iteration = -1;
+        dp->writer_busy = true;
         pthread_mutex_unlock(&dp->mu);
 
         int err = 0;
@@ -1307,6 +1309,9 @@ void *writer_main(void *arg)
         }
         /* scratch_busy was released when the last variable left HBM; by now the compute thread may
          * already own the scratch again for the next dump, so it must not be touched here */
+        dp->writer_busy = false;
+        if (err)
+            dp->scratch_busy = false;
         pthread_cond_broadcast(&dp->cv);
         pthread_mutex_unlock(&dp->mu);
     }
@@ -1443,11 +1448,17 @@ int fdtd_propagate(fdtd_ctx *c, const fdtd_dump_sink *sink, size_t *steps_done, 
         return FDTD_E_ARG;
     }
     if (sink) {
-        pipe_destroy(c);
-        int rc = pipe_create(c, sink);
-        if (rc != FDTD_OK) {
+        /* scratch, pinned buffers and the writer thread are kept for the life of the context:
+         * pinning two variable-sized host buffers is the expensive part (about 0.25 s per GB) */
+        if (c->pipe && !c->pipe->error) {
+            c->pipe->sink = *sink;
+        } else {
             pipe_destroy(c);
-            return rc;
+            int rc = pipe_create(c, sink);
+            if (rc != FDTD_OK) {
+                pipe_destroy(c);
+                return rc;
+            }
         }
     }
     int rc = FDTD_OK;
@@ -1483,14 +1494,17 @@ int fdtd_propagate(fdtd_ctx *c, const fdtd_dump_sink *sink, size_t *steps_done, 
     }
     if (rc == FDTD_OK)
         rc = fdtd_sync(c);
-    if (c->pipe) {
+    if (c->pipe && sink) {
         DumpPipe *dp = c->pipe;
-        pipe_join(dp); /* returns after the last sink.end() */
+        /* wait until the writer has delivered the last dump (its final sink.end()) */
+        pthread_mutex_lock(&dp->mu);
+        while ((dp->writer_busy || dp->pending_iteration >= 0) && !dp->error)
+            pthread_cond_wait(&dp->cv, &dp->mu);
         if (dp->error && rc == FDTD_OK) {
             rc = dp->error;
             fdtd_set_error("%s", dp->error_msg);
         }
-        pipe_destroy(c);
+        pthread_mutex_unlock(&dp->mu);
     }
     if (steps_done) *steps_done = steps;
     if (time_counter) *time_counter = t;

@@ -24,7 +24,7 @@ def test_energy_matches_oracle(F, oracle, dims):
         assert abs(h_gpu - h_ref) <= RTOL * abs(h_ref)
         # intended zone average of Ez: differs from the as-coded value on random fields, same H part
         e_int, h_int = ctx.energy(as_coded=False)
-        assert h_int == h_gpu and e_int != e_gpu
+        assert abs(h_int - h_gpu) <= RTOL * abs(h_gpu) and abs(e_int - e_gpu) > 1e-6 * abs(e_gpu)
         nx, ny, nz = q.dims()
         dv = q.spatial_step ** 3
         ez = f["ez"]
