@@ -140,8 +140,10 @@ def cpu_reference_rate(steps, warmup, nz=CPU_SAMPLE_NZ):
 
 
 def workload_config(n_gpus):
+    which = ("BASELINE.json configs[2]: 1024^3 per GPU" if (N_XY, NZ_PER_GPU) == (1024, 1024)
+             else "BASELINE.json configs[3]: 2048^3 class cavity in z-slabs" if N_XY == 2048 else "custom grid")
     return {"workload": f"{N_XY}x{N_XY}x{NZ_PER_GPU * n_gpus} PEC cavity, computation mode (waveguide source on), "
-                        f"dx=1mm dt=0.6ps, double precision (BASELINE.json configs[2]: 1024^3 per GPU)",
+                        f"dx=1mm dt=0.6ps, double precision ({which})",
             "cells": N_XY * N_XY * NZ_PER_GPU * n_gpus,
             "decomposition": f"{n_gpus} z-slab(s) of {NZ_PER_GPU} planes, one process per GPU",
             "l2": "state is 51.6 GB per GPU (held twice by the fused step), far larger than the 126 MB L2; no flush needed"}
@@ -168,13 +170,16 @@ def run_reference_arm(args):
 
 
 def main():
-    global NZ_PER_GPU
+    global NZ_PER_GPU, N_XY
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nz", type=int, default=NZ_PER_GPU, help="z cells per GPU (default: the 1024^3 workload)")
+    ap.add_argument("--nxy", type=int, default=N_XY, help="cells along x and y (default 1024)")
+    ap.add_argument("--nz-total", type=int, default=None,
+                    help="fixed total z cells split over the GPUs (strong scaling, e.g. 2048 with --nxy 2048)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="context option key=value (tuning)")
@@ -185,6 +190,7 @@ def main():
         return run_reference_arm(args)
 
     NZ_PER_GPU = args.nz
+    N_XY = args.nxy
     W = max(args.warmup, 3)
     K = args.steps
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -207,6 +213,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     nz_total = NZ_PER_GPU * world
+    if args.nz_total is not None:
+        nz_total = args.nz_total
+        NZ_PER_GPU = nz_total // world
     p = F.make_params(N_XY * DX, N_XY * DX, nz_total * DX, DX, DT, 1e-9, 1 << 30, 1)
     assert p.dims() == (N_XY, N_XY, nz_total), p.dims()
     ctx = F.Context(p, device=local, rank=rank, nranks=world)
@@ -317,7 +326,7 @@ def main():
     if rank == 0:
         line = {"metric": "cell_updates_per_second", "value": value, "unit": "Gcell-updates/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "scaling": "strong" if args.nz_total is not None else "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic (hash-pattern fields in HBM, waveguide source on)",
                 "config": dict(workload_config(world),
                                kernel={k: ctx.get_option(k) for k in ("kernel", "strip", "kchunk", "warps_x", "warps_y", "stages")}),

@@ -16,6 +16,7 @@ ap.add_argument("--n", type=int, default=1024)
 ap.add_argument("--nz", type=int, default=512)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--quick", action="store_true")
+ap.add_argument("--fine", action="store_true")
 ap.add_argument("--tma", action="store_true")
 ap.add_argument("--prefetch", action="store_true")
 ap.add_argument("--only", type=int, default=None, help="only this kernel id (plus the one-thread-per-cell reference)")
@@ -43,6 +44,12 @@ if args.tma:
     variants = [dict(kernel=0), dict(kernel=2, strip=1, kchunk=32, prefetch=3, warps_x=1, warps_y=4)]
     for strip, kchunk, stages, (wx, wy) in itertools.product((1, 2), (32, 128), (2, 3, 4, 6), [(1, 4), (1, 8), (2, 4), (2, 2), (4, 2), (4, 1), (8, 1)]):
         variants.append(dict(kernel=3, strip=strip, kchunk=kchunk, stages=stages, warps_x=wx, warps_y=wy))
+if args.fine:
+    variants = [dict(kernel=0)]
+    for strip, kchunk, stages, (wx, wy) in itertools.product((2,), (16, 32, 64, 128), (2, 3, 4), [(4, 2), (4, 1), (2, 2), (2, 4), (6, 1), (3, 2)]):
+        variants.append(dict(kernel=3, strip=strip, kchunk=kchunk, stages=stages, warps_x=wx, warps_y=wy))
+    for kchunk, stages, (wx, wy) in itertools.product((32, 64), (3, 4, 6), [(4, 2), (2, 4), (1, 8), (4, 1)]):
+        variants.append(dict(kernel=3, strip=1, kchunk=kchunk, stages=stages, warps_x=wx, warps_y=wy))
 if args.only is not None:
     variants = [v for v in variants if v["kernel"] == args.only or v["kernel"] == 0]
 
