@@ -541,6 +541,17 @@ int exchange_e(fdtd_ctx *c, cudaStream_t st, bool with_hz)
     return FDTD_OK;
 }
 
+/* Work on the compute stream that touches halo planes (dump exchange, diagnostics) must come after
+ * whatever the halo stream still has in flight from the last step. */
+int join_halo_stream(fdtd_ctx *c)
+{
+    if (c->nranks > 1) {
+        CUDA_TRY(cudaStreamWaitEvent(c->s_main, c->ev_ehalo, 0));
+        CUDA_TRY(cudaStreamWaitEvent(c->s_main, c->ev_hhalo, 0));
+    }
+    return FDTD_OK;
+}
+
 /* make the halos the selected kernel needs current, on the compute stream (after upload /
  * operator-level calls).  The flags are set identically on every rank, so the sends and
  * receives always pair up. */
@@ -549,6 +560,8 @@ int refresh_halos(fdtd_ctx *c)
     if (c->nranks == 1)
         return FDTD_OK;
     const bool fused = c->opt_kernel >= 2;
+    if (!c->e_halo_valid || !c->h_halo_valid || (fused && !c->low_e_halo_valid))
+        FDTD_TRY(join_halo_stream(c));
     if (!c->e_halo_valid) {
         FDTD_TRY(exchange_e(c, c->s_main, false));
         c->e_halo_valid = true;
@@ -1207,6 +1220,7 @@ int fdtd_aggregate(fdtd_ctx *c, int var, double *host_out)
     if (c->nranks > 1) {
         /* zone plane k1-1 of ex, ey, hz reads node plane k1 (main.c:517-520, 538-539) */
         c->e_halo_valid = false;
+        FDTD_TRY(join_halo_stream(c));
         FDTD_TRY(exchange_e(c, c->s_main, true));
         c->e_halo_valid = true;
     }
@@ -1414,6 +1428,7 @@ int post_dump(fdtd_ctx *c, int iteration, double t_validation)
     }
     if (c->nranks > 1) {
         c->e_halo_valid = false;
+        FDTD_TRY(join_halo_stream(c));
         FDTD_TRY(exchange_e(c, c->s_main, true)); /* node plane k1 of Ex, Ey, Hz for the top zone plane */
         c->e_halo_valid = true;
     }
@@ -1516,6 +1531,7 @@ int fdtd_energy(fdtd_ctx *c, int as_coded, double *e_energy, double *h_energy)
     FDTD_TRY(check_ctx(c, "fdtd_energy"));
     FDTD_TRY(use_device(c));
     if (c->nranks > 1) { /* the top zone plane averages with node plane k1 of Ex, Ey, Hz */
+        FDTD_TRY(join_halo_stream(c));
         FDTD_TRY(exchange_e(c, c->s_main, true));
         c->e_halo_valid = true;
     }

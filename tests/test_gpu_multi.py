@@ -125,3 +125,86 @@ def test_slabs_match_single_domain(dims, mode, steps, variant):
             pr.join(timeout=300)
             assert pr.exitcode == 0
         assert dict(ret) == {r: [] for r in range(world)}, f"world={world}"
+
+
+def _propagate_worker(rank, world, port, nums, ret):
+    import sys
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import fdtd_b200 as F
+    import oracle as O
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.cuda.set_device(rank)
+        path = f"/tmp/fdtd_multi_prop_{os.getpid()}.txt"
+        O.write_params(path, nums)
+        p, q = F.load_parameters(path), O.restatement().load_parameters(path)
+        o = O.restatement()
+        f = O.alloc_fields(*q.dims())
+        if q.mode == 0:
+            o.set_initial_conditions(q, f)
+        got = []
+        with F.Context(p, device=rank, rank=rank, nranks=world) as ctx:
+            box = [F.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            ctx.comm_init(box[0])
+            if q.mode == 0:
+                ctx.set_initial_conditions()
+            steps, _ = ctx.propagate(on_begin=lambda it, dims, k0: got.append({"it": it, "dims": dims, "k0": k0, "vars": {}}),
+                                     on_variable=lambda name, arr: got[-1]["vars"].__setitem__(name, arr))
+            k0, k1 = ctx.k0, ctx.k1
+        nx, ny, nz = q.dims()
+        names = ["ex", "ey", "ez", "hx", "hy", "hz"]
+
+        def expected(t_val):
+            out = {n: o.aggregate(q, f, v)[k0:k1] for v, n in enumerate(names)}
+            if q.mode == 0:
+                v = o.validation_fields(q, f, t_val)
+                out["aEy"] = o.aggregate(q, dict(f, ey=v["ey"]), 1)[k0:k1]
+                out["aHx"], out["aHz"] = out["hx"], out["hz"]   # as coded, main.c:585-588
+            return out
+
+        bad = []
+        want = [(1, expected(0.0))]
+        t, it = 0.0, 1
+        for _ in range(O.step_count(q)):
+            o.run(q, f, 1, t)
+            if it % q.sampling_rate == 0:
+                want.append((it, expected(t)))
+            t += q.time_step
+            it += 1
+        if steps != O.step_count(q) or [d["it"] for d in got] != [w[0] for w in want]:
+            bad.append(("cadence", [d["it"] for d in got]))
+        else:
+            for d, (it_w, vars_w) in zip(got, want):
+                if tuple(d["dims"]) != (nx, ny, k1 - k0) or d["k0"] != k0 or list(d["vars"]) != list(vars_w):
+                    bad.append(("shape", d["it"]))
+                    continue
+                for name, arr in vars_w.items():
+                    if not np.array_equal(d["vars"][name].view(np.uint64), arr.reshape(-1).view(np.uint64)):
+                        bad.append((d["it"], name))
+        ret[rank] = bad
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_slab_propagate_dumps_match_oracle(mode):
+    """fdtd_propagate on slabs: every rank dumps its own planes, same cadence, same contents
+    (incl. the zone plane that averages with the upper neighbour's node plane, and aEy)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import torch.multiprocessing as mp
+    nums = ("0.021", "0.017", "0.013", "0.001", "0.0000000000006", "0.000000000012", "4", str(mode))
+    world = 2
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_propagate_worker, args=(r, world, port, nums, ret)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(timeout=300)
+        assert pr.exitcode == 0
+    assert dict(ret) == {r: [] for r in range(world)}
