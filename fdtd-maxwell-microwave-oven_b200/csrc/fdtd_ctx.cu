@@ -843,6 +843,14 @@ int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx
     g.top = (rank == nranks - 1) ? 1 : 0;
     g.planes = g.nk + 2;
     c->array_elems = (size_t)g.PR * (size_t)g.planes;
+    /* launch-shape limits: the per-cell kernels put one plane per blockIdx.z, and the fused kernels
+     * index inside a plane with 32-bit offsets */
+    if (g.planes > 65535 || g.PR >= (1LL << 31) - 4 * (long long)g.P) {
+        fdtd_set_error("fdtd_ctx_create: slab of %d planes of %d x %d is outside the supported launch shapes "
+                       "(at most 65533 planes per slab, plane below 2^31 elements)", g.nk, g.I, g.J);
+        delete c;
+        return FDTD_E_ARG;
+    }
     c->ch = fdtd_factor_h(p);
     c->ce = fdtd_factor_e(p);
     /* default: the TMA-staged fused step with the launch shape that won the sweep on a B200
