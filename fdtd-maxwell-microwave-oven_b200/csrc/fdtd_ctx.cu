@@ -429,7 +429,7 @@ int encode_maps(fdtd_ctx *c, int bx, int by)
     return FDTD_OK;
 }
 
-template <int TY>
+template <int TY, int CWX, int CWY>
 int launch_fused_tma_t(fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStream_t st)
 {
     const int wx = (int)c->opt_wx, wy = (int)c->opt_wy;
@@ -437,21 +437,35 @@ int launch_fused_tma_t(fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cuda
     FDTD_TRY(encode_maps(c, bx, by));
     const int stages = (int)c->opt_stages;
     const size_t smem = (size_t)stages * 6 * tma_box_doubles(bx, by) * sizeof(double);
-    static size_t configured = 0;
-    if (smem > configured) {
-        CUDA_TRY(cudaFuncSetAttribute(k_step_fused_tma<TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-        configured = 227 * 1024;
-    }
     if (smem > 226 * 1024) {
         fdtd_set_error("TMA ring of %d stages x %d x %d tile needs %zu bytes of shared memory", stages, bx, by, smem);
         return FDTD_E_ARG;
     }
+    static bool configured = false; /* one flag per instantiation */
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(k_step_fused_tma<TY, CWX, CWY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      226 * 1024));
+        configured = true;
+    }
     Span sp{kl_begin, kl_end, (int)std::max(c->opt_kchunk, 2L), 0};
     dim3 block(bx, wy);
     dim3 grid((c->g.I + 1 + bx - 1) / bx, (c->g.J + 1 + by - 1) / by, (kl_end - kl_begin + sp.kchunk - 1) / sp.kchunk);
-    k_step_fused_tma<TY><<<grid, block, smem, st>>>(c->g, c->tma_maps[0], c->f2, c->ch, c->ce, s, sp, stages);
+    k_step_fused_tma<TY, CWX, CWY><<<grid, block, smem, st>>>(c->g, c->tma_maps[0], c->f2, c->ch, c->ce, s, sp, stages);
     ++c->launches;
     return FDTD_OK;
+}
+
+/* the launch shapes that won the sweeps get a kernel with the shape baked in; any other shape runs
+ * the generic instantiation */
+int launch_fused_tma(fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStream_t st)
+{
+    const long ty = c->opt_strip == 1 ? 1 : 2, wx = c->opt_wx, wy = c->opt_wy;
+    if (ty == 2 && wx == 4 && wy == 2) return launch_fused_tma_t<2, 4, 2>(c, s, kl_begin, kl_end, st);
+    if (ty == 2 && wx == 2 && wy == 2) return launch_fused_tma_t<2, 2, 2>(c, s, kl_begin, kl_end, st);
+    if (ty == 2 && wx == 2 && wy == 4) return launch_fused_tma_t<2, 2, 4>(c, s, kl_begin, kl_end, st);
+    if (ty == 1 && wx == 1 && wy == 8) return launch_fused_tma_t<1, 1, 8>(c, s, kl_begin, kl_end, st);
+    if (ty == 2) return launch_fused_tma_t<2, 0, 0>(c, s, kl_begin, kl_end, st);
+    return launch_fused_tma_t<1, 0, 0>(c, s, kl_begin, kl_end, st);
 }
 
 /* one whole step (H then E) of the local planes [kl_begin, kl_end): reads c->f, writes c->f2 */
@@ -460,11 +474,7 @@ void launch_fused(fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStrea
     if (kl_end <= kl_begin)
         return;
     if (c->opt_kernel == 3) {
-        int rc;
-        switch (c->opt_strip) {
-        case 1: rc = launch_fused_tma_t<1>(c, s, kl_begin, kl_end, st); break;
-        default: rc = launch_fused_tma_t<2>(c, s, kl_begin, kl_end, st); break;
-        }
+        const int rc = launch_fused_tma(c, s, kl_begin, kl_end, st);
         if (rc != FDTD_OK)
             c->launch_error = rc;
         return;

@@ -92,14 +92,16 @@ __host__ __device__ inline int tma_box_doubles(int bx, int by)
 
 constexpr int kTmaMaxStages = 8;
 
-template <int TY, bool EDGE>
+/* CWX, CWY: block shape in warps (32*CWX x CWY threads) known at compile time, so that every
+ * shared-memory offset is an immediate; 0 = read the shape from blockDim (any launch shape). */
+template <int TY, bool EDGE, int CWX, int CWY>
 __device__ __forceinline__ void fused_tma_sweep(const Geo &g, const TmaMaps &maps, const Fld &b,
                                                 const double cH, const double cE, const Src &s,
                                                 const int stages, double *ring, unsigned long long *full,
                                                 const int bx0, const int by0, const int kl0, const int kl1)
 {
     constexpr int NR = TY + 2;
-    const int BX = blockDim.x, BY = blockDim.y * TY;
+    const int BX = CWX ? 32 * CWX : (int)blockDim.x, BY = (CWY ? CWY : (int)blockDim.y) * TY;
     const int W = BX + 4;
     const int box = tma_box_doubles(BX, BY);
     const int stage_doubles = 6 * box;
@@ -192,10 +194,20 @@ __device__ __forceinline__ void fused_tma_sweep(const Geo &g, const TmaMaps &map
     for (int r = 0; r < TY; ++r)
         hxm[r] = hym[r] = 0.0;
 
+    /* A warp whose 32 columns all lie beyond column I (the last block in x usually holds the single
+     * column i = I) has nothing to compute: it only keeps the block barriers company. */
+    const bool warp_has_work = !EDGE || (i - (int)lane) <= g.I;
+
     long long pl = (long long)kstart * g.PR;
     for (int kl = kstart, n = 0; kl < kl1; ++kl, ++n, pl += g.PR) {
         const bool srck = s.on && kl == 1;
         const int slot = n % stages, slot1 = (n + 1) % stages;
+        if (!warp_has_work) {
+            __syncthreads();
+            if (leader && n + stages < nplanes)
+                issue(n + stages);
+            continue;
+        }
         /* stage n was awaited one iteration ago (for its Ex, Ey) or above (n = 0) */
         tma::mbar_wait(full + slot1, (unsigned)(((n + 1) / stages) & 1));
         const double *cur = ring + (size_t)slot * stage_doubles;
@@ -364,7 +376,7 @@ __device__ __forceinline__ void fused_tma_sweep(const Geo &g, const TmaMaps &map
     }
 }
 
-template <int TY>
+template <int TY, int CWX, int CWY>
 __global__ void __launch_bounds__(256, 2)
 k_step_fused_tma(Geo g, const __grid_constant__ TmaMaps maps, Fld b, double cH, double cE, Src s, Span sp,
                  int stages)
@@ -389,9 +401,9 @@ k_step_fused_tma(Geo g, const __grid_constant__ TmaMaps maps, Fld b, double cH, 
     const bool interior = bx0 >= 1 && bx0 + (int)blockDim.x <= g.I && by0 >= 1 &&
                           by0 + (int)blockDim.y * TY <= g.J;
     if (interior)
-        fused_tma_sweep<TY, false>(g, maps, b, cH, cE, s, stages, ring, full, bx0, by0, kl0, kl1);
+        fused_tma_sweep<TY, false, CWX, CWY>(g, maps, b, cH, cE, s, stages, ring, full, bx0, by0, kl0, kl1);
     else
-        fused_tma_sweep<TY, true>(g, maps, b, cH, cE, s, stages, ring, full, bx0, by0, kl0, kl1);
+        fused_tma_sweep<TY, true, CWX, CWY>(g, maps, b, cH, cE, s, stages, ring, full, bx0, by0, kl0, kl1);
 }
 
 } /* namespace fdtd */
