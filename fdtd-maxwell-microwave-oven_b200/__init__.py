@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfdtd_b200.so")
+LIB_PATH = os.environ.get("FDTD_B200_LIB") or os.path.join(HERE, "libfdtd_b200.so")  # override: A/B of two builds
 FIELD_NAMES = ("Ex", "Ey", "Ez", "Hx", "Hy", "Hz")
 DUMP_NAMES = ("ex", "ey", "ez", "hx", "hy", "hz")
 

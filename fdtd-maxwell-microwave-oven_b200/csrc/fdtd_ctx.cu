@@ -161,7 +161,7 @@ int check_ctx(const fdtd_ctx *c, const char *who)
         fdtd_set_error("%s: context is NULL", who);
         return FDTD_E_ARG;
     }
-    if (c->opt_wx * c->opt_wy > 8) { /* a block is at most 256 threads */
+    if (c->opt_wx * c->opt_wy > (c->opt_kernel == 3 ? 16 : 8)) { /* a block is at most 256 threads (512 for the TMA kernel) */
         fdtd_set_error("%s: options warps_x (%ld) * warps_y (%ld) must be <= 8", who, c->opt_wx, c->opt_wy);
         return FDTD_E_ARG;
     }
@@ -463,6 +463,12 @@ int launch_fused_tma(fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaSt
     if (ty == 2 && wx == 4 && wy == 2) return launch_fused_tma_t<2, 4, 2>(c, s, kl_begin, kl_end, st);
     if (ty == 2 && wx == 2 && wy == 2) return launch_fused_tma_t<2, 2, 2>(c, s, kl_begin, kl_end, st);
     if (ty == 2 && wx == 2 && wy == 4) return launch_fused_tma_t<2, 2, 4>(c, s, kl_begin, kl_end, st);
+    if (ty == 2 && wx == 4 && wy == 4) return launch_fused_tma_t<2, 4, 4>(c, s, kl_begin, kl_end, st); /* 512 threads */
+    if (ty == 2 && wx == 2 && wy == 8) return launch_fused_tma_t<2, 2, 8>(c, s, kl_begin, kl_end, st); /* 512 threads */
+    if (wx * wy > 8) {
+        fdtd_set_error("TMA kernel: %ld x %ld warps has no 512-thread instantiation (use 4x4 or 2x8 with strip 2)", wx, wy);
+        return FDTD_E_ARG;
+    }
     if (ty == 1 && wx == 1 && wy == 8) return launch_fused_tma_t<1, 1, 8>(c, s, kl_begin, kl_end, st);
     if (ty == 2) return launch_fused_tma_t<2, 0, 0>(c, s, kl_begin, kl_end, st);
     return launch_fused_tma_t<1, 0, 0>(c, s, kl_begin, kl_end, st);

@@ -134,10 +134,10 @@ __device__ __forceinline__ void fused_tma_sweep(const Geo &g, const TmaMaps &map
     const unsigned full_bytes = 6u * (unsigned)(W * (BY + 2)) * 8u;
     const unsigned last_bytes = 2u * (unsigned)(W * (BY + 2)) * 8u;
 
-    /* producer: plane kstart + n into slot n % stages */
-    auto issue = [&](int n) {
-        double *dst = ring + (size_t)(n % stages) * stage_doubles;
-        unsigned long long *bar = full + (n % stages);
+    /* producer: plane kstart + n into ring slot `slot` (= n mod stages, tracked without dividing) */
+    auto issue = [&](int slot, int n) {
+        double *dst = ring + (size_t)slot * stage_doubles;
+        unsigned long long *bar = full + slot;
         const int plane = kstart + n;
         const bool last = n == nplanes - 1;
         tma::mbar_expect_tx(bar, last ? last_bytes : full_bytes);
@@ -152,7 +152,7 @@ __device__ __forceinline__ void fused_tma_sweep(const Geo &g, const TmaMaps &map
     };
     if (leader) {
         for (int n = 0; n < stages && n < nplanes; ++n)
-            issue(n);
+            issue(n, n);
     }
 
     /* position of (i, jb-1) inside a box: column tx+2, row ty*TY */
@@ -199,18 +199,28 @@ __device__ __forceinline__ void fused_tma_sweep(const Geo &g, const TmaMaps &map
     const bool warp_has_work = !EDGE || (i - (int)lane) <= g.I;
 
     long long pl = (long long)kstart * g.PR;
+    int slot = 0;        /* ring slot of plane kl */
+    unsigned phase = 0;  /* mbarrier phase parity of that slot's current fill */
     for (int kl = kstart, n = 0; kl < kl1; ++kl, ++n, pl += g.PR) {
         const bool srck = s.on && kl == 1;
-        const int slot = n % stages, slot1 = (n + 1) % stages;
+        int slot1 = slot + 1;
+        unsigned phase1 = phase;
+        if (slot1 == stages) {
+            slot1 = 0;
+            phase1 ^= 1u;
+        }
+        const int slot_now = slot;
+        slot = slot1;
+        phase = phase1;
         if (!warp_has_work) {
             __syncthreads();
             if (leader && n + stages < nplanes)
-                issue(n + stages);
+                issue(slot_now, n + stages);
             continue;
         }
         /* stage n was awaited one iteration ago (for its Ex, Ey) or above (n = 0) */
-        tma::mbar_wait(full + slot1, (unsigned)(((n + 1) / stages) & 1));
-        const double *cur = ring + (size_t)slot * stage_doubles;
+        tma::mbar_wait(full + slot1, phase1);
+        const double *cur = ring + (size_t)slot_now * stage_doubles;
         const double *nxt = ring + (size_t)slot1 * stage_doubles;
         const double *sexn = nxt, *seyn = nxt + box;
         const double *sez = cur + 2 * box, *shx = cur + 3 * box, *shy = cur + 4 * box, *shz = cur + 5 * box;
@@ -320,7 +330,7 @@ __device__ __forceinline__ void fused_tma_sweep(const Geo &g, const TmaMaps &map
         /* every thread has taken what it needs from stage n: hand the slot back to the producer */
         __syncthreads();
         if (leader && n + stages < nplanes)
-            issue(n + stages);
+            issue(slot_now, n + stages);
 
         if (kl >= kl0) {
             const bool cell = kl <= g.nk;
@@ -376,8 +386,9 @@ __device__ __forceinline__ void fused_tma_sweep(const Geo &g, const TmaMaps &map
     }
 }
 
+/* 256-thread blocks, two per SM -- or one 512-thread block for the largest tiles */
 template <int TY, int CWX, int CWY>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__((CWX * CWY > 8) ? 512 : 256, (CWX * CWY > 8) ? 1 : 2)
 k_step_fused_tma(Geo g, const __grid_constant__ TmaMaps maps, Fld b, double cH, double cE, Src s, Span sp,
                  int stages)
 {

@@ -16,6 +16,7 @@ ap.add_argument("--n", type=int, default=1024)
 ap.add_argument("--nz", type=int, default=512)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--quick", action="store_true")
+ap.add_argument("--big", action="store_true")
 ap.add_argument("--fine", action="store_true")
 ap.add_argument("--tma", action="store_true")
 ap.add_argument("--prefetch", action="store_true")
@@ -50,6 +51,11 @@ if args.fine:
         variants.append(dict(kernel=3, strip=strip, kchunk=kchunk, stages=stages, warps_x=wx, warps_y=wy))
     for kchunk, stages, (wx, wy) in itertools.product((32, 64), (3, 4, 6), [(4, 2), (2, 4), (1, 8), (4, 1)]):
         variants.append(dict(kernel=3, strip=1, kchunk=kchunk, stages=stages, warps_x=wx, warps_y=wy))
+if args.big:
+    variants = [dict(kernel=3, strip=2, kchunk=32, stages=3, warps_x=4, warps_y=2)]
+    for kchunk, stages, (wx, wy) in itertools.product((32, 64), (2, 3), [(4, 4), (2, 8)]):
+        variants.append(dict(kernel=3, strip=2, kchunk=kchunk, stages=stages, warps_x=wx, warps_y=wy))
+    variants.append(dict(kernel=3, strip=2, kchunk=32, stages=3, warps_x=4, warps_y=2))
 if args.only is not None:
     variants = [v for v in variants if v["kernel"] == args.only or v["kernel"] == 0]
 
