@@ -278,3 +278,44 @@ def test_linearity_power_of_two_scaling(F, oracle):
         fa, fb = a.download(), b.download()
         for k in fa:
             assert bits_equal(2.0 * fa[k], fb[k]), k
+
+
+def test_random_shapes_and_launch_configs(F, oracle):
+    """40 seeded random cavities (1..70 cells per axis, both modes where the source patch fits) x random
+    kernel / strip / chunk / tile / ring settings, 1-6 steps from a random state: all bit-exact."""
+    o = oracle.restatement()
+    rng = np.random.default_rng(20261018)
+    done = 0
+    while done < 40:
+        nx, ny, nz = (int(v) for v in rng.integers(1, 71, size=3))
+        mode = int(rng.integers(0, 2))
+        dims = ((nx + .5) * 1e-3, (ny + .5) * 1e-3, (nz + .5) * 1e-3)
+        p = F.make_params(*dims, 0.001, 6e-13, 1.2e-10, 2, mode)
+        assert p.dims() == (nx, ny, nz)
+        if mode == 1:
+            plan = F.source_plan(p)
+            if plan.i0 < 0 or plan.j0 < 0 or plan.i1 > nx or plan.j1 > ny:
+                continue
+        kernel = int(rng.integers(0, 4))
+        variant = dict(kernel=kernel, kchunk=int(rng.choice([1, 2, 3, 7, 32, 1000])))
+        if kernel == 1:
+            wx, wy = [(1, 8), (2, 4), (4, 2), (8, 1), (2, 2), (1, 1)][int(rng.integers(0, 6))]
+            variant.update(strip=int(rng.choice([1, 2, 4])), warps_x=wx, warps_y=wy)
+        elif kernel == 2:
+            wx, wy = [(1, 4), (2, 2), (4, 1), (1, 2), (1, 1)][int(rng.integers(0, 5))]
+            variant.update(strip=int(rng.integers(1, 5)), warps_x=wx, warps_y=wy, prefetch=int(rng.integers(0, 5)))
+        elif kernel == 3:
+            wx, wy = [(1, 8), (2, 4), (4, 2), (2, 2), (1, 4), (4, 4), (3, 2), (1, 1)][int(rng.integers(0, 8))]
+            variant.update(strip=2 if wx * wy > 8 else int(rng.integers(1, 3)), warps_x=wx, warps_y=wy,
+                           stages=int(rng.integers(2, 7)))
+        steps = int(rng.integers(1, 7))
+        q = to_oracle_params(oracle, p)
+        f = random_state(oracle, q, int(rng.integers(0, 1 << 30)))
+        with F.Context(p) as ctx:
+            configure(ctx, variant)
+            ctx.upload(upper(f))
+            t_gpu = ctx.run(steps, 0.0)
+            t_cpu = o.run(q, f, steps)
+            assert t_gpu == t_cpu
+            assert_fields_equal(ctx.download(), f, f"{(nx, ny, nz)} mode {mode} {variant} {steps} steps")
+        done += 1
