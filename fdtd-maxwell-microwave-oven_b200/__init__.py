@@ -98,6 +98,17 @@ SIGNATURES = {
     "fdtd_sync": (C.c_int, [_CTX]),
     "fdtd_aggregate": (C.c_int, [_CTX, C.c_int, _D]),
     "fdtd_propagate": (C.c_int, [_CTX, C.POINTER(DumpSink), C.POINTER(C.c_size_t), _D]),
+    "fdtd_group_create": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
+    "fdtd_group_destroy": (C.c_int, [C.c_void_p]),
+    "fdtd_group_size": (C.c_int, [C.c_void_p]),
+    "fdtd_group_ctx": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_CTX)]),
+    "fdtd_group_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_long]),
+    "fdtd_group_upload": (C.c_int, [C.c_void_p, C.POINTER(FieldPtrs)]),
+    "fdtd_group_download": (C.c_int, [C.c_void_p, C.POINTER(FieldPtrs)]),
+    "fdtd_group_set_initial_conditions": (C.c_int, [C.c_void_p]),
+    "fdtd_group_run": (C.c_int, [C.c_void_p, C.c_size_t, _D]),
+    "fdtd_group_sync": (C.c_int, [C.c_void_p]),
+    "fdtd_group_propagate": (C.c_int, [C.c_void_p, C.POINTER(DumpSink), C.POINTER(C.c_size_t), _D]),
     "fdtd_energy": (C.c_int, [_CTX, C.c_int, _D, _D]),
     "fdtd_validation_error": (C.c_int, [_CTX, C.c_double, _D, _D]),
     "fdtd_fill_test_pattern": (C.c_int, [_CTX, C.c_ulonglong]),
@@ -379,6 +390,90 @@ class Context:
 
         sink = DumpSink(None, _BEGIN(_begin), _VARIABLE(_variable), _END(_end))
         _check(lib.fdtd_propagate(self._h, C.byref(sink), C.byref(steps), C.byref(tc)))
+        return int(steps.value), tc.value
+
+
+class Group:
+    """fdtd_group: every z-slab of the cavity driven from this one thread (no launcher)."""
+
+    def __init__(self, p: Params, ngpus, devices=None):
+        self.p = p
+        self._g = C.c_void_p()
+        dev = (C.c_int * ngpus)(*devices) if devices is not None else None
+        _check(lib.fdtd_group_create(C.byref(p), ngpus, dev, C.byref(self._g)))
+        self.n = lib.fdtd_group_size(self._g)
+        self.slabs = []
+        for r in range(self.n):
+            h = _CTX()
+            _check(lib.fdtd_group_ctx(self._g, r, C.byref(h)))
+            ctx = Context.__new__(Context)      # a view: the group owns the context
+            ctx.p, ctx._h, ctx.rank, ctx.nranks = p, h, r, self.n
+            ctx.k0, ctx.k1 = slab_range(int(p.maxk), r, self.n)
+            ctx.close = lambda: None
+            self.slabs.append(ctx)
+
+    def close(self):
+        if self._g:
+            for s in self.slabs:
+                s._h = _CTX()
+            lib.fdtd_group_destroy(self._g)
+            self._g = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_option(self, key, value):
+        _check(lib.fdtd_group_set_option(self._g, key.encode(), int(value)))
+
+    def upload(self, fields):
+        _check(lib.fdtd_group_upload(self._g, C.byref(_ptrs(fields))))
+
+    def download(self, out=None):
+        if out is None:
+            out = {n: np.zeros(s) for n, s in field_shapes(self.p).items()}
+        _check(lib.fdtd_group_download(self._g, C.byref(_ptrs(out))))
+        return out
+
+    def set_initial_conditions(self):
+        _check(lib.fdtd_group_set_initial_conditions(self._g))
+
+    def run(self, steps, t=0.0):
+        tc = C.c_double(t)
+        _check(lib.fdtd_group_run(self._g, int(steps), C.byref(tc)))
+        return tc.value
+
+    def sync(self):
+        _check(lib.fdtd_group_sync(self._g))
+
+    def propagate(self, on_begin=None, on_variable=None, on_end=None, dumps=True):
+        """callbacks get the slab rank as first argument; they run on per-slab writer threads"""
+        steps, tc = C.c_size_t(), C.c_double()
+        if not dumps:
+            _check(lib.fdtd_group_propagate(self._g, None, C.byref(steps), C.byref(tc)))
+            return int(steps.value), tc.value
+        keep, sinks = [], (DumpSink * self.n)()
+        for r in range(self.n):
+            def _begin(user, iteration, dims, k0, r=r):
+                if on_begin:
+                    on_begin(r, iteration, (dims[0], dims[1], dims[2]), k0)
+                return 0
+
+            def _variable(user, name, data, count, r=r):
+                if on_variable:
+                    on_variable(r, name.decode(), np.ctypeslib.as_array(data, shape=(count,)).copy())
+                return 0
+
+            def _end(user, r=r):
+                if on_end:
+                    on_end(r)
+                return 0
+            cbs = (_BEGIN(_begin), _VARIABLE(_variable), _END(_end))
+            keep.append(cbs)
+            sinks[r] = DumpSink(None, *cbs)
+        _check(lib.fdtd_group_propagate(self._g, sinks, C.byref(steps), C.byref(tc)))
         return int(steps.value), tc.value
 
 

@@ -5,66 +5,16 @@
  * in the pitched layout described in fdtd_kernels.cuh, a compute stream, a halo stream with its
  * NCCL communicator, and a dump stream with pinned staging.  The host control thread only
  * queues work; nothing on the stepping path synchronises with the device.
- */
-#include "fdtd_internal.h"
-#include "fdtd_kernels.cuh"
+ */#include "fdtd_ctx.hpp"
+#include "fdtd_update.cuh"
 #include "fdtd_fused.cuh"
 #include "fdtd_fused_tma.cuh"
 
-#include <dlfcn.h>
-#include <nccl.h>
-#include <pthread.h>
+using namespace fdtdi;
 
-#include <algorithm>
-#include <cmath>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <vector>
+namespace fdtdi {
 
-using namespace fdtd;
-
-#define CUDA_TRY(expr)                                                                         \
-    do {                                                                                       \
-        cudaError_t e_ = (expr);                                                               \
-        if (e_ != cudaSuccess) {                                                               \
-            fdtd_set_error("%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
-            return FDTD_E_CUDA;                                                                \
-        }                                                                                      \
-    } while (0)
-
-#define NCCL_TRY(expr)                                                                         \
-    do {                                                                                       \
-        ncclResult_t r_ = (expr);                                                              \
-        if (r_ != ncclSuccess) {                                                               \
-            fdtd_set_error("%s: %s (%s:%d)", #expr, g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
-            return FDTD_E_NCCL;                                                                \
-        }                                                                                      \
-    } while (0)
-
-#define FDTD_TRY(expr)                                                                         \
-    do {                                                                                       \
-        int rc_ = (expr);                                                                      \
-        if (rc_ != FDTD_OK)                                                                    \
-            return rc_;                                                                        \
-    } while (0)
-
-namespace {
-
-/* NCCL is bound at run time, on first multi-GPU use, instead of at link time: a process that has
- * already loaded a libnccl.so.2 (e.g. the one PyTorch ships) keeps using that very library, and a
- * single-GPU run never loads NCCL at all. */
-struct NcclApi {
-    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
-    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
-    ncclResult_t (*CommDestroy)(ncclComm_t);
-    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
-    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
-    ncclResult_t (*GroupStart)(void);
-    ncclResult_t (*GroupEnd)(void);
-    const char *(*GetErrorString)(ncclResult_t);
-    bool ok;
-} g_nccl;
+NcclApi g_nccl;
 
 int nccl_bind()
 {
@@ -79,6 +29,7 @@ int nccl_bind()
 #define BIND(field, sym) *(void **)(&g_nccl.field) = dlsym(h, sym)
             BIND(GetUniqueId, "ncclGetUniqueId");
             BIND(CommInitRank, "ncclCommInitRank");
+            BIND(CommInitAll, "ncclCommInitAll");
             BIND(CommDestroy, "ncclCommDestroy");
             BIND(Send, "ncclSend");
             BIND(Recv, "ncclRecv");
@@ -86,7 +37,7 @@ int nccl_bind()
             BIND(GroupEnd, "ncclGroupEnd");
             BIND(GetErrorString, "ncclGetErrorString");
 #undef BIND
-            g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.Send &&
+            g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommInitAll && g_nccl.CommDestroy && g_nccl.Send &&
                         g_nccl.Recv && g_nccl.GroupStart && g_nccl.GroupEnd && g_nccl.GetErrorString;
         }
     }
@@ -99,61 +50,6 @@ int nccl_bind()
     return FDTD_OK;
 }
 
-constexpr int kSrcRing = 512; /* source rows (steps) resident on the device at a time */
-
-struct DumpPipe;
-
-} /* namespace */
-
-struct fdtd_ctx {
-    fdtd_params p;
-    int device, rank, nranks;
-    size_t k0, k1;
-    Geo g;
-    Fld f;
-    double *base;       /* the six arrays of the current state, inside raw (guard margins either side) */
-    double *base2;      /* second set for the fused single-sweep step ("kernel" = 2), allocated on demand */
-    double *raw, *raw2; /* what cudaMalloc returned */
-    Fld f2;
-    size_t array_elems; /* P * R * planes */
-    double ch, ce;      /* update factors, main.c:441 / :479 */
-
-    cudaStream_t s_main, s_comm, s_dump;
-    cudaEvent_t ev_hb, ev_eb, ev_hhalo, ev_ehalo;
-    bool e_halo_valid, h_halo_valid;
-    bool low_e_halo_valid; /* fused step only: plane 0 also holds the lower neighbour's Ex, Ey, Ez */
-    ncclComm_t comm;
-    bool has_comm;
-
-    /* source */
-    fdtd_source_plan plan;
-    int src_n;          /* points per row */
-    bool src_here;      /* computation mode and this slab holds k = 0 */
-    double *src_dev;    /* kSrcRing rows of 2*src_n doubles */
-    double *src_host;   /* pinned mirror */
-    cudaEvent_t ev_src; /* last upload of the ring finished */
-    double *src_one_dev; /* single row for the operator-level fdtd_set_source */
-
-    /* options */
-    long opt_kernel, opt_strip, opt_kchunk, opt_wx, opt_wy, opt_prefetch, opt_stages;
-
-    /* tensor maps of the TMA-staged fused step: [buffer set][array], valid for tma_bx x tma_by tiles */
-    TmaMaps tma_maps[2];
-    double *tma_base[2];
-    int tma_bx, tma_by;
-    mutable long launches; /* kernels of this library launched so far (reports) */
-    int launch_error;      /* first failure inside a launch helper, reported by queue_step */
-    bool kernel_auto;      /* "kernel" was not chosen by the caller: may fall back to the split kernels */
-
-    /* dump scratch for fdtd_aggregate */
-    double *agg_dev;
-    size_t agg_elems;
-
-    /* asynchronous dump pipeline (fdtd_propagate) */
-    DumpPipe *pipe;
-};
-
-namespace {
 
 int check_ctx(const fdtd_ctx *c, const char *who)
 {
@@ -179,11 +75,6 @@ double *field_ptr(const fdtd_ctx *c, int idx)
     return c->base + (size_t)idx * c->array_elems;
 }
 
-/* dense host shape of each array: row length, rows, planes (main.c:379-407); node = has K+1 planes */
-struct DenseShape {
-    size_t w, h, d;
-    bool node_planes;
-};
 
 DenseShape dense_shape(const fdtd_params &p, int idx)
 {
@@ -590,27 +481,33 @@ int refresh_halos(fdtd_ctx *c)
     return FDTD_OK;
 }
 
-/* One pass of the loop body main.c:770-779 with the halo traffic hidden behind the interior
- * planes: the boundary plane is updated first, its event releases the halo stream, the
- * interior follows on the compute stream. */
-int queue_step(fdtd_ctx *c, const Src &s, cudaEvent_t ev_h_begin, cudaEvent_t ev_mid, cudaEvent_t ev_e_end)
+/* A time step is made of segments -- one for the fused kernels (H and E in one sweep), two for the
+ * split kernels (H half-step, E half-step).  Each segment has three parts so that several slabs
+ * driven by ONE host thread (fdtd_group_*) can put all their NCCL calls of a segment into a single
+ * NCCL group:
+ *   seg_launch    everything on the compute stream: wait for the halos of the previous segment,
+ *                 boundary plane(s) first, event, interior planes; the halo stream is told to wait
+ *                 for the boundary event (the halo traffic hides behind the interior planes);
+ *   seg_exchange  the ncclSend / ncclRecv calls on the halo stream;
+ *   seg_finish    the "halo has arrived" events the next segment waits for. */
+int seg_launch(fdtd_ctx *c, const Src &s, Segment seg)
 {
+    FDTD_TRY(use_device(c));
     const int nk = c->g.nk;
     const int h_end = nk + c->g.top + 1; /* exclusive */
-    if (ev_h_begin)
-        CUDA_TRY(cudaEventRecord(ev_h_begin, c->s_main));
-
-    if (c->opt_kernel >= 2) {
-        /* fused: one sweep does H and E; reads c->f, writes c->f2, then the two swap */
-        if (c->nranks == 1) {
+    const bool multi = c->nranks > 1;
+    const bool sends_up = c->rank + 1 < c->nranks, sends_down = c->rank > 0;
+    if (seg == SEG_FUSED) {
+        /* reads c->f, writes c->f2, then the two swap */
+        if (!multi) {
             launch_fused(c, s, 1, h_end, c->s_main);
             swap_buffers(c);
         } else {
             CUDA_TRY(cudaStreamWaitEvent(c->s_main, c->ev_ehalo, 0));
             CUDA_TRY(cudaStreamWaitEvent(c->s_main, c->ev_hhalo, 0));
-            const bool sends_up = c->rank + 1 < c->nranks, sends_down = c->rank > 0;
             if (nk < 3) {
                 launch_fused(c, s, 1, h_end, c->s_main);
+                CUDA_TRY(cudaEventRecord(c->ev_hb, c->s_main));
             } else {
                 int lo = 1, hi = h_end;
                 if (sends_up) { /* top owned plane first: 5 arrays of it travel up */
@@ -624,72 +521,105 @@ int queue_step(fdtd_ctx *c, const Src &s, cudaEvent_t ev_h_begin, cudaEvent_t ev
                 CUDA_TRY(cudaEventRecord(c->ev_hb, c->s_main));
                 launch_fused(c, s, lo, hi, c->s_main);
             }
-            if (nk < 3)
-                CUDA_TRY(cudaEventRecord(c->ev_hb, c->s_main));
-            swap_buffers(c); /* the exchange below works on the new state */
+            swap_buffers(c); /* the exchange works on the new state */
             CUDA_TRY(cudaStreamWaitEvent(c->s_comm, c->ev_hb, 0));
-            FDTD_TRY(exchange_h(c, c->s_comm, true));
-            FDTD_TRY(exchange_e(c, c->s_comm, false));
-            CUDA_TRY(cudaEventRecord(c->ev_hhalo, c->s_comm));
-            CUDA_TRY(cudaEventRecord(c->ev_ehalo, c->s_comm));
         }
-        if (ev_mid)
-            CUDA_TRY(cudaEventRecord(ev_mid, c->s_main));
-        if (ev_e_end)
-            CUDA_TRY(cudaEventRecord(ev_e_end, c->s_main));
         if (c->launch_error != FDTD_OK) {
             const int rc = c->launch_error;
             c->launch_error = FDTD_OK;
             return rc;
         }
-        CUDA_TRY(cudaGetLastError());
-        return FDTD_OK;
-    }
-
-    if (c->opt_kernel == 0 && c->src_here)
-        launch_set_source(c, s.vals, c->s_main);
-    if (c->nranks == 1) {
-        launch_h(c, s, 1, h_end, c->s_main);
-    } else {
-        CUDA_TRY(cudaStreamWaitEvent(c->s_main, c->ev_ehalo, 0)); /* Ex, Ey of plane nk+1 arrived */
-        const bool sends_up = c->rank + 1 < c->nranks;
-        if (sends_up) {
-            launch_h(c, s, nk, nk + 1, c->s_main); /* boundary plane first */
-            CUDA_TRY(cudaEventRecord(c->ev_hb, c->s_main));
-            launch_h(c, s, 1, nk, c->s_main);
-        } else {
+    } else if (seg == SEG_H) {
+        if (c->opt_kernel == 0 && c->src_here)
+            launch_set_source(c, s.vals, c->s_main);
+        if (!multi) {
             launch_h(c, s, 1, h_end, c->s_main);
-            CUDA_TRY(cudaEventRecord(c->ev_hb, c->s_main));
-        }
-        CUDA_TRY(cudaStreamWaitEvent(c->s_comm, c->ev_hb, 0));
-        FDTD_TRY(exchange_h(c, c->s_comm, false));
-        CUDA_TRY(cudaEventRecord(c->ev_hhalo, c->s_comm));
-    }
-    if (ev_mid)
-        CUDA_TRY(cudaEventRecord(ev_mid, c->s_main));
-    if (c->opt_kernel == 0 && c->src_here)
-        launch_set_source(c, s.vals, c->s_main);
-    if (c->nranks == 1) {
-        launch_e(c, s, 1, nk + 1, c->s_main);
-    } else {
-        CUDA_TRY(cudaStreamWaitEvent(c->s_main, c->ev_hhalo, 0)); /* Hx, Hy of plane 0 arrived */
-        const bool sends_down = c->rank > 0;
-        if (sends_down) {
-            launch_e(c, s, 1, 2, c->s_main);
-            CUDA_TRY(cudaEventRecord(c->ev_eb, c->s_main));
-            launch_e(c, s, 2, nk + 1, c->s_main);
         } else {
-            launch_e(c, s, 1, nk + 1, c->s_main);
-            CUDA_TRY(cudaEventRecord(c->ev_eb, c->s_main));
+            CUDA_TRY(cudaStreamWaitEvent(c->s_main, c->ev_ehalo, 0)); /* Ex, Ey of plane nk+1 arrived */
+            if (sends_up) {
+                launch_h(c, s, nk, nk + 1, c->s_main); /* boundary plane first */
+                CUDA_TRY(cudaEventRecord(c->ev_hb, c->s_main));
+                launch_h(c, s, 1, nk, c->s_main);
+            } else {
+                launch_h(c, s, 1, h_end, c->s_main);
+                CUDA_TRY(cudaEventRecord(c->ev_hb, c->s_main));
+            }
+            CUDA_TRY(cudaStreamWaitEvent(c->s_comm, c->ev_hb, 0));
         }
-        CUDA_TRY(cudaStreamWaitEvent(c->s_comm, c->ev_eb, 0));
+    } else {
+        if (c->opt_kernel == 0 && c->src_here)
+            launch_set_source(c, s.vals, c->s_main);
+        if (!multi) {
+            launch_e(c, s, 1, nk + 1, c->s_main);
+        } else {
+            CUDA_TRY(cudaStreamWaitEvent(c->s_main, c->ev_hhalo, 0)); /* Hx, Hy of plane 0 arrived */
+            if (sends_down) {
+                launch_e(c, s, 1, 2, c->s_main);
+                CUDA_TRY(cudaEventRecord(c->ev_eb, c->s_main));
+                launch_e(c, s, 2, nk + 1, c->s_main);
+            } else {
+                launch_e(c, s, 1, nk + 1, c->s_main);
+                CUDA_TRY(cudaEventRecord(c->ev_eb, c->s_main));
+            }
+            CUDA_TRY(cudaStreamWaitEvent(c->s_comm, c->ev_eb, 0));
+        }
+        c->low_e_halo_valid = false; /* the split kernels refresh only Hx, Hy of plane 0 */
+    }
+    CUDA_TRY(cudaGetLastError());
+    return FDTD_OK;
+}
+
+int seg_exchange(fdtd_ctx *c, Segment seg)
+{
+    if (c->nranks == 1)
+        return FDTD_OK;
+    FDTD_TRY(use_device(c));
+    if (seg == SEG_FUSED) {
+        FDTD_TRY(exchange_h(c, c->s_comm, true));
         FDTD_TRY(exchange_e(c, c->s_comm, false));
+    } else if (seg == SEG_H) {
+        FDTD_TRY(exchange_h(c, c->s_comm, false));
+    } else {
+        FDTD_TRY(exchange_e(c, c->s_comm, false));
+    }
+    return FDTD_OK;
+}
+
+int seg_finish(fdtd_ctx *c, Segment seg)
+{
+    if (c->nranks == 1)
+        return FDTD_OK;
+    FDTD_TRY(use_device(c));
+    if (seg == SEG_FUSED || seg == SEG_H)
+        CUDA_TRY(cudaEventRecord(c->ev_hhalo, c->s_comm));
+    if (seg == SEG_FUSED || seg == SEG_E)
         CUDA_TRY(cudaEventRecord(c->ev_ehalo, c->s_comm));
+    return FDTD_OK;
+}
+
+/* One pass of the loop body main.c:770-779 for one context (one process per GPU). */
+int queue_step(fdtd_ctx *c, const Src &s, cudaEvent_t ev_h_begin, cudaEvent_t ev_mid, cudaEvent_t ev_e_end)
+{
+    if (ev_h_begin)
+        CUDA_TRY(cudaEventRecord(ev_h_begin, c->s_main));
+    if (c->opt_kernel >= 2) {
+        FDTD_TRY(seg_launch(c, s, SEG_FUSED));
+        FDTD_TRY(seg_exchange(c, SEG_FUSED));
+        FDTD_TRY(seg_finish(c, SEG_FUSED));
+        if (ev_mid)
+            CUDA_TRY(cudaEventRecord(ev_mid, c->s_main));
+    } else {
+        FDTD_TRY(seg_launch(c, s, SEG_H));
+        FDTD_TRY(seg_exchange(c, SEG_H));
+        FDTD_TRY(seg_finish(c, SEG_H));
+        if (ev_mid)
+            CUDA_TRY(cudaEventRecord(ev_mid, c->s_main));
+        FDTD_TRY(seg_launch(c, s, SEG_E));
+        FDTD_TRY(seg_exchange(c, SEG_E));
+        FDTD_TRY(seg_finish(c, SEG_E));
     }
     if (ev_e_end)
         CUDA_TRY(cudaEventRecord(ev_e_end, c->s_main));
-    CUDA_TRY(cudaGetLastError());
-    c->low_e_halo_valid = false; /* the split kernels refresh only Hx, Hy of plane 0 */
     return FDTD_OK;
 }
 
@@ -714,20 +644,26 @@ int stage_source_rows(fdtd_ctx *c, size_t count, double *t_io)
     return FDTD_OK;
 }
 
+/* The fused step needs the state twice in HBM; when that does not fit and the caller did not ask
+ * for a particular kernel, the in-place split kernels (144 B per cell-update instead of 96) take
+ * over -- still on the GPU. */
+void fall_back_to_split(fdtd_ctx *c)
+{
+    cudaGetLastError();
+    c->opt_kernel = 1;
+    c->opt_strip = 2;
+    c->opt_kchunk = 8;
+    c->opt_wx = 2;
+    c->opt_wy = 2;
+}
+
 int run_impl(fdtd_ctx *c, size_t steps, double *time_counter, float *total_ms, float *h_ms, float *e_ms)
 {
     FDTD_TRY(use_device(c));
     if (c->opt_kernel >= 2) {
         int rc = ensure_pong(c);
         if (rc == FDTD_E_NOMEM && c->kernel_auto) {
-            /* the fused step needs the state twice in HBM; when that does not fit, the in-place
-             * split kernels (144 B per cell-update instead of 96) take over -- still on the GPU */
-            cudaGetLastError();
-            c->opt_kernel = 1;
-            c->opt_strip = 2;
-            c->opt_kchunk = 8;
-            c->opt_wx = 2;
-            c->opt_wy = 2;
+            fall_back_to_split(c);
         } else if (rc != FDTD_OK) {
             return rc;
         }
@@ -941,12 +877,11 @@ int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx
     return FDTD_OK;
 }
 
-void pipe_destroy(fdtd_ctx *c);
 
-} /* namespace */
+} /* namespace fdtdi */
+
 
 /* ============================================ C ABI ========================================= */
-
 extern "C" {
 
 int fdtd_ctx_create(const fdtd_params *p, int device, fdtd_ctx **out)
@@ -1224,465 +1159,6 @@ int fdtd_sync(fdtd_ctx *c)
     CUDA_TRY(cudaStreamSynchronize(c->s_dump));
     return FDTD_OK;
 }
-
-int fdtd_aggregate(fdtd_ctx *c, int var, double *host_out)
-{
-    FDTD_TRY(check_ctx(c, "fdtd_aggregate"));
-    if (var < 0 || var > 5 || !host_out) {
-        fdtd_set_error("fdtd_aggregate: bad argument (var %d)", var);
-        return FDTD_E_ARG;
-    }
-    FDTD_TRY(use_device(c));
-    const size_t n = (size_t)c->g.I * c->g.J * c->g.nk;
-    if (c->agg_elems < n) {
-        if (c->agg_dev) cudaFree(c->agg_dev);
-        c->agg_dev = nullptr;
-        c->agg_elems = 0;
-        CUDA_TRY(cudaMalloc((void **)&c->agg_dev, n * sizeof(double)));
-        c->agg_elems = n;
-    }
-    if (c->nranks > 1) {
-        /* zone plane k1-1 of ex, ey, hz reads node plane k1 (main.c:517-520, 538-539) */
-        c->e_halo_valid = false;
-        FDTD_TRY(join_halo_stream(c));
-        FDTD_TRY(exchange_e(c, c->s_main, true));
-        c->e_halo_valid = true;
-    }
-    dim3 block(64, 4);
-    dim3 grid((c->g.I + 63) / 64, (c->g.J + 3) / 4, c->g.nk);
-    k_aggregate<<<grid, block, 0, c->s_main>>>(c->g, field_ptr(c, var), var, c->agg_dev);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(host_out, c->agg_dev, n * sizeof(double), cudaMemcpyDeviceToHost, c->s_main));
-    CUDA_TRY(cudaStreamSynchronize(c->s_main));
-    return FDTD_OK;
-}
-
-} /* extern "C" */
-
-/* ===================================== dumps: fdtd_propagate ================================= */
-
-namespace {
-
-constexpr int kMaxDumpVars = 9;
-const char *const kVarNames[kMaxDumpVars] = {"ex", "ey", "ez", "hx", "hy", "hz", "aEy", "aHx", "aHz"};
-
-/* Writer-side state.  The compute thread aggregates every variable of one dump into HBM scratch
- * (dev[v]) on the compute stream and posts the iteration number; the writer thread drains the
- * scratch through two pinned buffers on the dump stream and feeds the sink.  The compute thread
- * blocks only if the next dump is due before the previous one has left HBM. */
-struct DumpPipe {
-    fdtd_ctx *ctx;
-    fdtd_dump_sink sink;
-    size_t n;                   /* doubles per variable */
-    int nvars;                  /* 6 or 9 */
-    double *dev[7];             /* ex..hz, aEy (aHx/aHz alias hx/hz, main.c:585-588) */
-    double *pinned[2];
-    cudaEvent_t ev_agg, ev_copy[2];
-    double *sk_dev, *si_dev;    /* analytic factors for aEy */
-    double f_mnl;
-
-    pthread_t thread;
-    pthread_mutex_t mu;
-    pthread_cond_t cv;
-    int pending_iteration;      /* -1: none */
-    bool scratch_busy;          /* dev[] still being drained */
-    bool writer_busy;           /* a dump is between sink.begin and sink.end */
-    bool stop;
-    int error;                  /* first sink / CUDA failure seen by the writer */
-    char error_msg[256];
-};
-
-void *writer_main(void *arg)
-{
-    DumpPipe *dp = (DumpPipe *)arg;
-    fdtd_ctx *c = dp->ctx;
-    cudaSetDevice(c->device);
-    for (;;) {
-        pthread_mutex_lock(&dp->mu);
-        while (dp->pending_iteration < 0 && !dp->stop)
-            pthread_cond_wait(&dp->cv, &dp->mu);
-        if (dp->pending_iteration < 0 && dp->stop) {
-            pthread_mutex_unlock(&dp->mu);
-            return nullptr;
-        }
-        const int iteration = dp->pending_iteration;
-        dp->pending_iteration = -1;
-        dp->writer_busy = true;
-        pthread_mutex_unlock(&dp->mu);
-
-        int err = 0;
-        const char *what = "";
-        const size_t dims[3] = {(size_t)c->g.I, (size_t)c->g.J, (size_t)c->g.nk};
-        if (cudaStreamWaitEvent(c->s_dump, dp->ev_agg, 0) != cudaSuccess) { err = FDTD_E_CUDA; what = "wait for aggregation"; }
-        if (!err && dp->sink.begin && dp->sink.begin(dp->sink.user, iteration, dims, c->k0) != 0) { err = FDTD_E_IO; what = "sink.begin"; }
-        auto source_of = [&](int v) { return v < 7 ? dp->dev[v] : (v == 7 ? dp->dev[3] : dp->dev[5]); };
-        auto start_copy = [&](int v) {
-            if (cudaMemcpyAsync(dp->pinned[v & 1], source_of(v), dp->n * sizeof(double), cudaMemcpyDeviceToHost, c->s_dump) != cudaSuccess ||
-                cudaEventRecord(dp->ev_copy[v & 1], c->s_dump) != cudaSuccess) {
-                err = FDTD_E_CUDA;
-                what = "device-to-host copy";
-            }
-        };
-        if (!err)
-            start_copy(0);
-        for (int v = 0; v < dp->nvars && !err; ++v) {
-            if (cudaEventSynchronize(dp->ev_copy[v & 1]) != cudaSuccess) { err = FDTD_E_CUDA; what = "device-to-host copy"; break; }
-            if (v + 1 < dp->nvars)
-                start_copy(v + 1); /* overlaps with the sink consuming variable v */
-            else {
-                /* the last variable has left HBM: the compute thread may aggregate the next dump */
-                pthread_mutex_lock(&dp->mu);
-                dp->scratch_busy = false;
-                pthread_cond_broadcast(&dp->cv);
-                pthread_mutex_unlock(&dp->mu);
-            }
-            if (!err && dp->sink.variable &&
-                dp->sink.variable(dp->sink.user, kVarNames[v], dp->pinned[v & 1], dp->n) != 0) { err = FDTD_E_IO; what = "sink.variable"; }
-        }
-        if (!err && dp->sink.end && dp->sink.end(dp->sink.user) != 0) { err = FDTD_E_IO; what = "sink.end"; }
-        pthread_mutex_lock(&dp->mu);
-        if (err && !dp->error) {
-            dp->error = err;
-            snprintf(dp->error_msg, sizeof dp->error_msg, "dump of iteration %d failed in %s", iteration, what);
-        }
-        /* scratch_busy was released when the last variable left HBM; by now the compute thread may
-         * already own the scratch again for the next dump, so it must not be touched here */
-        dp->writer_busy = false;
-        if (err)
-            dp->scratch_busy = false;
-        pthread_cond_broadcast(&dp->cv);
-        pthread_mutex_unlock(&dp->mu);
-    }
-}
-
-int pipe_create(fdtd_ctx *c, const fdtd_dump_sink *sink)
-{
-    DumpPipe *dp = new (std::nothrow) DumpPipe();
-    if (!dp) {
-        fdtd_set_error("fdtd_propagate: out of host memory");
-        return FDTD_E_NOMEM;
-    }
-    memset(dp, 0, sizeof *dp);
-    c->pipe = dp;
-    dp->ctx = c;
-    dp->sink = *sink;
-    dp->n = (size_t)c->g.I * c->g.J * c->g.nk;
-    dp->nvars = c->p.mode == 0 ? 9 : 6;
-    dp->pending_iteration = -1;
-    const int ndev = c->p.mode == 0 ? 7 : 6;
-    for (int v = 0; v < ndev; ++v)
-        CUDA_TRY(cudaMalloc((void **)&dp->dev[v], dp->n * sizeof(double)));
-    for (int b = 0; b < 2; ++b) {
-        CUDA_TRY(cudaHostAlloc((void **)&dp->pinned[b], dp->n * sizeof(double), cudaHostAllocDefault));
-        CUDA_TRY(cudaEventCreateWithFlags(&dp->ev_copy[b], cudaEventDisableTiming));
-    }
-    CUDA_TRY(cudaEventCreateWithFlags(&dp->ev_agg, cudaEventDisableTiming));
-    if (c->p.mode == 0) {
-        /* factors of the analytic TE101 solution, main.c:672 and :688-690, with the host libm */
-        const fdtd_params &p = c->p;
-        std::vector<double> sk(p.maxk + 2), si(p.maxi + 2);
-        for (size_t k = 0; k < p.maxk + 1; ++k)
-            sk[k] = sin(FDTD_PI * k * p.spatial_step / p.height);
-        for (size_t i = 0; i < p.maxi + 1; ++i)
-            si[i] = sin(FDTD_PI * i * p.spatial_step / p.length);
-        dp->f_mnl = 0.5 * FDTD_CELERITY * sqrt(pow(FDTD_PI / p.height, 2) + pow(FDTD_PI / p.length, 2)) / FDTD_PI;
-        CUDA_TRY(cudaMalloc((void **)&dp->sk_dev, sk.size() * sizeof(double)));
-        CUDA_TRY(cudaMalloc((void **)&dp->si_dev, si.size() * sizeof(double)));
-        CUDA_TRY(cudaMemcpy(dp->sk_dev, sk.data(), sk.size() * sizeof(double), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(dp->si_dev, si.data(), si.size() * sizeof(double), cudaMemcpyHostToDevice));
-    }
-    pthread_mutex_init(&dp->mu, nullptr);
-    pthread_cond_init(&dp->cv, nullptr);
-    if (pthread_create(&dp->thread, nullptr, writer_main, dp) != 0) {
-        fdtd_set_error("fdtd_propagate: cannot start the writer thread");
-        return FDTD_E_STATE;
-    }
-    return FDTD_OK;
-}
-
-/* let the writer finish what is queued, then stop it */
-void pipe_join(DumpPipe *dp)
-{
-    if (!dp->thread)
-        return;
-    pthread_mutex_lock(&dp->mu);
-    dp->stop = true;
-    pthread_cond_broadcast(&dp->cv);
-    pthread_mutex_unlock(&dp->mu);
-    pthread_join(dp->thread, nullptr);
-    dp->thread = 0;
-    pthread_mutex_destroy(&dp->mu);
-    pthread_cond_destroy(&dp->cv);
-}
-
-void pipe_destroy(fdtd_ctx *c)
-{
-    DumpPipe *dp = c->pipe;
-    if (!dp)
-        return;
-    pipe_join(dp);
-    for (int v = 0; v < 7; ++v)
-        if (dp->dev[v]) cudaFree(dp->dev[v]);
-    for (int b = 0; b < 2; ++b) {
-        if (dp->pinned[b]) cudaFreeHost(dp->pinned[b]);
-        if (dp->ev_copy[b]) cudaEventDestroy(dp->ev_copy[b]);
-    }
-    if (dp->ev_agg) cudaEventDestroy(dp->ev_agg);
-    if (dp->sk_dev) cudaFree(dp->sk_dev);
-    if (dp->si_dev) cudaFree(dp->si_dev);
-    delete dp;
-    c->pipe = nullptr;
-}
-
-/* write_silo(), main.c:550-598, device side: aggregate every variable of the current state.
- * t_validation is the time the validation fields were last evaluated for (main.c:762, :783). */
-int post_dump(fdtd_ctx *c, int iteration, double t_validation)
-{
-    DumpPipe *dp = c->pipe;
-    pthread_mutex_lock(&dp->mu);
-    while (dp->scratch_busy && !dp->error)
-        pthread_cond_wait(&dp->cv, &dp->mu);
-    const int err = dp->error;
-    if (!err)
-        dp->scratch_busy = true;
-    pthread_mutex_unlock(&dp->mu);
-    if (err) {
-        fdtd_set_error("%s", dp->error_msg);
-        return err;
-    }
-    if (c->nranks > 1) {
-        c->e_halo_valid = false;
-        FDTD_TRY(join_halo_stream(c));
-        FDTD_TRY(exchange_e(c, c->s_main, true)); /* node plane k1 of Ex, Ey, Hz for the top zone plane */
-        c->e_halo_valid = true;
-    }
-    dim3 block(64, 4);
-    dim3 grid((c->g.I + 63) / 64, (c->g.J + 3) / 4, c->g.nk);
-    for (int v = 0; v < 6; ++v)
-        k_aggregate<<<grid, block, 0, c->s_main>>>(c->g, field_ptr(c, v), v, dp->dev[v]);
-    if (c->p.mode == 0) {
-        const double ct = cos(2 * FDTD_PI * dp->f_mnl * t_validation); /* main.c:688 */
-        k_aggregate_aey<<<grid, block, 0, c->s_main>>>(c->g, c->f.ey, ct, dp->sk_dev, dp->si_dev, dp->dev[6]);
-    }
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(dp->ev_agg, c->s_main));
-    pthread_mutex_lock(&dp->mu);
-    dp->pending_iteration = iteration;
-    pthread_cond_broadcast(&dp->cv);
-    pthread_mutex_unlock(&dp->mu);
-    return FDTD_OK;
-}
-
-} /* namespace */
-
-extern "C" {
-
-int fdtd_propagate(fdtd_ctx *c, const fdtd_dump_sink *sink, size_t *steps_done, double *time_counter)
-{
-    FDTD_TRY(check_ctx(c, "fdtd_propagate"));
-    FDTD_TRY(use_device(c));
-    if (sink && c->p.sampling_rate == 0) {
-        /* the reference divides by zero at main.c:794 */
-        fdtd_set_error("fdtd_propagate: sampling_rate must be >= 1");
-        return FDTD_E_ARG;
-    }
-    if (sink) {
-        /* scratch, pinned buffers and the writer thread are kept for the life of the context:
-         * pinning two variable-sized host buffers is the expensive part (about 0.25 s per GB) */
-        if (c->pipe && !c->pipe->error) {
-            c->pipe->sink = *sink;
-        } else {
-            pipe_destroy(c);
-            int rc = pipe_create(c, sink);
-            if (rc != FDTD_OK) {
-                pipe_destroy(c);
-                return rc;
-            }
-        }
-    }
-    int rc = FDTD_OK;
-    int iteration = 1; /* main.c:758 */
-    size_t steps = 0;
-    double t = 0.0;
-    if (sink)
-        rc = post_dump(c, iteration, 0.0); /* main.c:762-764 */
-    /* main.c:765: double counter, repeated addition, float bound promoted to double, `<=` */
-    while (rc == FDTD_OK && t <= c->p.simulation_time) {
-        /* queue every step up to the next dump in one go */
-        size_t batch = 0;
-        double t_probe = t, t_last = t;
-        int it_probe = iteration;
-        while (t_probe <= c->p.simulation_time) {
-            ++batch;
-            t_last = t_probe;
-            t_probe += c->p.time_step;
-            if (sink && it_probe % (int)c->p.sampling_rate == 0)
-                break;
-            ++it_probe;
-            if (!sink && batch >= 4096)
-                break;
-        }
-        rc = run_impl(c, batch, &t, nullptr, nullptr, nullptr);
-        if (rc != FDTD_OK)
-            break;
-        steps += batch;
-        iteration += (int)batch;
-        /* main.c:794: the test runs before `iteration++`, i.e. on the index of the pass just done */
-        if (sink && (iteration - 1) % (int)c->p.sampling_rate == 0)
-            rc = post_dump(c, iteration - 1, t_last);
-    }
-    if (rc == FDTD_OK)
-        rc = fdtd_sync(c);
-    if (c->pipe && sink) {
-        DumpPipe *dp = c->pipe;
-        /* wait until the writer has delivered the last dump (its final sink.end()) */
-        pthread_mutex_lock(&dp->mu);
-        while ((dp->writer_busy || dp->pending_iteration >= 0) && !dp->error)
-            pthread_cond_wait(&dp->cv, &dp->mu);
-        if (dp->error && rc == FDTD_OK) {
-            rc = dp->error;
-            fdtd_set_error("%s", dp->error_msg);
-        }
-        pthread_mutex_unlock(&dp->mu);
-    }
-    if (steps_done) *steps_done = steps;
-    if (time_counter) *time_counter = t;
-    return rc;
-}
-
-int fdtd_energy(fdtd_ctx *c, int as_coded, double *e_energy, double *h_energy)
-{
-    FDTD_TRY(check_ctx(c, "fdtd_energy"));
-    FDTD_TRY(use_device(c));
-    if (c->nranks > 1) { /* the top zone plane averages with node plane k1 of Ex, Ey, Hz */
-        FDTD_TRY(join_halo_stream(c));
-        FDTD_TRY(exchange_e(c, c->s_main, true));
-        c->e_halo_valid = true;
-    }
-    double *dev = nullptr;
-    CUDA_TRY(cudaMalloc((void **)&dev, 6 * sizeof(double)));
-    cudaMemsetAsync(dev, 0, 6 * sizeof(double), c->s_main);
-    dim3 block(64, 4);
-    dim3 grid((c->g.I + 63) / 64, (c->g.J + 3) / 4, c->g.nk);
-    k_energy<<<grid, block, 0, c->s_main>>>(c->g, c->f, as_coded, dev);
-    double s[6];
-    cudaError_t e = cudaMemcpyAsync(s, dev, sizeof s, cudaMemcpyDeviceToHost, c->s_main);
-    if (e == cudaSuccess)
-        e = cudaStreamSynchronize(c->s_main);
-    cudaFree(dev);
-    if (e != cudaSuccess) {
-        fdtd_set_error("fdtd_energy: %s", cudaGetErrorString(e));
-        return FDTD_E_CUDA;
-    }
-    const double dv = pow(c->p.spatial_step, 3); /* main.c:613 */
-    if (e_energy) *e_energy = (s[0] * dv + s[1] * dv + s[2] * dv) * FDTD_EPSILON / 2.; /* main.c:631 */
-    if (h_energy) *h_energy = (s[3] * dv + s[4] * dv + s[5] * dv) * FDTD_MU / 2.;      /* main.c:665 */
-    return FDTD_OK;
-}
-
-int fdtd_validation_error(fdtd_ctx *c, double t, double sums[6], double rel_l2[3])
-{
-    FDTD_TRY(check_ctx(c, "fdtd_validation_error"));
-    FDTD_TRY(use_device(c));
-    const fdtd_params &p = c->p;
-    const size_t nk = p.maxk + 2, ni = p.maxi + 2;
-    std::vector<double> tab(2 * nk + 2 * ni);
-    double *sk = tab.data(), *ck = sk + nk, *si = ck + nk, *ci = si + ni;
-    for (size_t k = 0; k < p.maxk + 1; ++k) {
-        sk[k] = sin(FDTD_PI * k * p.spatial_step / p.height);
-        ck[k] = cos(FDTD_PI * k * p.spatial_step / p.height);
-    }
-    for (size_t i = 0; i < p.maxi + 1; ++i) {
-        si[i] = sin(FDTD_PI * i * p.spatial_step / p.length);
-        ci[i] = cos(FDTD_PI * i * p.spatial_step / p.length);
-    }
-    /* main.c:672-675 */
-    const double f_mnl = 0.5 * FDTD_CELERITY * sqrt(pow(FDTD_PI / p.height, 2) + pow(FDTD_PI / p.length, 2)) / FDTD_PI;
-    const double omega = 2.0 * FDTD_PI * f_mnl;
-    const double z_te = (omega * FDTD_MU) / sqrt(pow(omega, 2) * FDTD_MU * FDTD_EPSILON - pow(FDTD_PI / p.length, 2));
-    const double a_ey = cos(2 * FDTD_PI * f_mnl * t);
-    const double a_hx = (1.0 / z_te) * sin(2 * FDTD_PI * f_mnl * t);
-    const double a_hz = -FDTD_PI / (omega * FDTD_MU * p.length) * sin(2 * FDTD_PI * f_mnl * t);
-    double *dev = nullptr;
-    CUDA_TRY(cudaMalloc((void **)&dev, (tab.size() + 6) * sizeof(double)));
-    cudaError_t e = cudaMemcpyAsync(dev + 6, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, c->s_main);
-    cudaMemsetAsync(dev, 0, 6 * sizeof(double), c->s_main);
-    dim3 block(64, 4);
-    dim3 grid((c->g.I + 1 + 63) / 64, (c->g.J + 3) / 4, c->g.nk + c->g.top);
-    k_validation_error<<<grid, block, 0, c->s_main>>>(c->g, c->f, dev + 6, dev + 6 + nk, dev + 6 + 2 * nk,
-                                                     dev + 6 + 2 * nk + ni, a_ey, a_hx, a_hz, c->g.top, dev);
-    double s[6];
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(s, dev, sizeof s, cudaMemcpyDeviceToHost, c->s_main);
-    if (e == cudaSuccess)
-        e = cudaStreamSynchronize(c->s_main);
-    cudaFree(dev);
-    if (e != cudaSuccess) {
-        fdtd_set_error("fdtd_validation_error: %s", cudaGetErrorString(e));
-        return FDTD_E_CUDA;
-    }
-    for (int v = 0; v < 6; ++v)
-        if (sums) sums[v] = s[v];
-    for (int v = 0; v < 3; ++v)
-        if (rel_l2) rel_l2[v] = s[2 * v + 1] > 0.0 ? sqrt(s[2 * v] / s[2 * v + 1]) : 0.0;
-    return FDTD_OK;
-}
-
-static DenseView dense_view(const fdtd_ctx *c, int idx)
-{
-    const DenseShape s = dense_shape(c->p, idx);
-    DenseView v;
-    v.w = (int)s.w;
-    v.h = (int)s.h;
-    v.np = c->g.nk + ((s.node_planes && c->g.top) ? 1 : 0);
-    v.kd0 = (long long)c->k0;
-    return v;
-}
-
-int fdtd_fill_test_pattern(fdtd_ctx *c, unsigned long long seed)
-{
-    FDTD_TRY(check_ctx(c, "fdtd_fill_test_pattern"));
-    FDTD_TRY(use_device(c));
-    CUDA_TRY(cudaMemsetAsync(c->base, 0, 6 * c->array_elems * sizeof(double), c->s_main));
-    for (int a = 0; a < 6; ++a) {
-        const DenseView v = dense_view(c, a);
-        dim3 block(64, 4);
-        dim3 grid((v.w + 63) / 64, (v.h + 3) / 4, v.np);
-        k_fill_pattern<<<grid, block, 0, c->s_main>>>(c->g, field_ptr(c, a), v, seed, a);
-    }
-    CUDA_TRY(cudaGetLastError());
-    c->e_halo_valid = c->h_halo_valid = c->low_e_halo_valid = (c->nranks == 1);
-    return FDTD_OK;
-}
-
-int fdtd_checksum(fdtd_ctx *c, unsigned long long out[6])
-{
-    FDTD_TRY(check_ctx(c, "fdtd_checksum"));
-    if (!out) {
-        fdtd_set_error("fdtd_checksum: NULL argument");
-        return FDTD_E_ARG;
-    }
-    FDTD_TRY(use_device(c));
-    unsigned long long *dev = nullptr;
-    CUDA_TRY(cudaMalloc((void **)&dev, 6 * sizeof(unsigned long long)));
-    cudaMemsetAsync(dev, 0, 6 * sizeof(unsigned long long), c->s_main);
-    for (int a = 0; a < 6; ++a) {
-        const DenseView v = dense_view(c, a);
-        dim3 block(64, 4);
-        dim3 grid((v.w + 63) / 64, (v.h + 3) / 4, v.np);
-        k_checksum<<<grid, block, 0, c->s_main>>>(c->g, field_ptr(c, a), v, dev + a);
-    }
-    cudaError_t e = cudaMemcpyAsync(out, dev, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->s_main);
-    if (e == cudaSuccess)
-        e = cudaStreamSynchronize(c->s_main);
-    cudaFree(dev);
-    if (e != cudaSuccess) {
-        fdtd_set_error("fdtd_checksum: %s", cudaGetErrorString(e));
-        return FDTD_E_CUDA;
-    }
-    return FDTD_OK;
-}
-
 int fdtd_host_alloc(size_t bytes, void **out)
 {
     if (!out) {

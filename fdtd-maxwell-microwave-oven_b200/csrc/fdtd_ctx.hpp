@@ -1,0 +1,162 @@
+/*
+ * fdtd_ctx.hpp -- the device context and what the translation units of libfdtd_b200.so share:
+ * fdtd_ctx.cu (context, transfers, launches, halo exchange, stepping), fdtd_dump.cu (dump variables,
+ * fdtd_propagate), fdtd_diag.cu (energy, analytic-mode error, test pattern, checksum).
+ */
+#pragma once
+
+#include "fdtd_internal.h"
+#include "fdtd_types.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+#include <pthread.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+using namespace fdtd;
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            fdtd_set_error("%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return FDTD_E_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+#define NCCL_TRY(expr)                                                                         \
+    do {                                                                                       \
+        ncclResult_t r_ = (expr);                                                              \
+        if (r_ != ncclSuccess) {                                                               \
+            fdtd_set_error("%s: %s (%s:%d)", #expr, g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
+            return FDTD_E_NCCL;                                                                \
+        }                                                                                      \
+    } while (0)
+
+#define FDTD_TRY(expr)                                                                         \
+    do {                                                                                       \
+        int rc_ = (expr);                                                                      \
+        if (rc_ != FDTD_OK)                                                                    \
+            return rc_;                                                                        \
+    } while (0)
+
+namespace fdtdi {
+
+/* NCCL is bound at run time, on first multi-GPU use, instead of at link time: a process that has
+ * already loaded a libnccl.so.2 (e.g. the one PyTorch ships) keeps using that very library, and a
+ * single-GPU run never loads NCCL at all. */struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)(void);
+    ncclResult_t (*GroupEnd)(void);
+    const char *(*GetErrorString)(ncclResult_t);
+    bool ok;
+};
+extern NcclApi g_nccl;
+int nccl_bind();
+
+constexpr int kSrcRing = 512; /* source rows (steps) resident on the device at a time */
+
+struct DumpPipe;
+
+} /* namespace fdtdi */
+
+struct fdtd_ctx {
+    fdtd_params p;
+    int device, rank, nranks;
+    size_t k0, k1;
+    Geo g;
+    Fld f;
+    double *base;       /* the six arrays of the current state, inside raw (guard margins either side) */
+    double *base2;      /* second set for the fused single-sweep step ("kernel" = 2), allocated on demand */
+    double *raw, *raw2; /* what cudaMalloc returned */
+    Fld f2;
+    size_t array_elems; /* P * R * planes */
+    double ch, ce;      /* update factors, main.c:441 / :479 */
+
+    cudaStream_t s_main, s_comm, s_dump;
+    cudaEvent_t ev_hb, ev_eb, ev_hhalo, ev_ehalo;
+    bool e_halo_valid, h_halo_valid;
+    bool low_e_halo_valid; /* fused step only: plane 0 also holds the lower neighbour's Ex, Ey, Ez */
+    ncclComm_t comm;
+    bool has_comm;
+
+    /* source */
+    fdtd_source_plan plan;
+    int src_n;          /* points per row */
+    bool src_here;      /* computation mode and this slab holds k = 0 */
+    double *src_dev;    /* kSrcRing rows of 2*src_n doubles */
+    double *src_host;   /* pinned mirror */
+    cudaEvent_t ev_src; /* last upload of the ring finished */
+    double *src_one_dev; /* single row for the operator-level fdtd_set_source */
+
+    /* options */
+    long opt_kernel, opt_strip, opt_kchunk, opt_wx, opt_wy, opt_prefetch, opt_stages;
+
+    /* tensor maps of the TMA-staged fused step: [buffer set][array], valid for tma_bx x tma_by tiles */
+    TmaMaps tma_maps[2];
+    double *tma_base[2];
+    int tma_bx, tma_by;
+    mutable long launches; /* kernels of this library launched so far (reports) */
+    int launch_error;      /* first failure inside a launch helper, reported by queue_step */
+    bool kernel_auto;      /* "kernel" was not chosen by the caller: may fall back to the split kernels */
+
+    /* dump scratch for fdtd_aggregate */
+    double *agg_dev;
+    size_t agg_elems;
+
+    /* asynchronous dump pipeline (fdtd_propagate) */
+    fdtdi::DumpPipe *pipe;
+};
+
+namespace fdtdi {
+
+int check_ctx(const fdtd_ctx *c, const char *who);
+int use_device(const fdtd_ctx *c);
+double *field_ptr(const fdtd_ctx *c, int idx);
+
+/* dense host shape of each array: row length, rows, planes (main.c:379-407); node = has K+1 planes */
+struct DenseShape {
+    size_t w, h, d;
+    bool node_planes;
+};
+DenseShape dense_shape(const fdtd_params &p, int idx);
+
+int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx **out);
+int ensure_pong(fdtd_ctx *c);
+void fall_back_to_split(fdtd_ctx *c);
+fdtd::Src make_src(const fdtd_ctx *c, const double *row);
+int stage_source_rows(fdtd_ctx *c, size_t count, double *t_io);
+
+/* halo exchange: the NCCL calls only (may sit inside a caller's NCCL group) */
+int exchange_h(fdtd_ctx *c, cudaStream_t st, bool with_e);
+int exchange_e(fdtd_ctx *c, cudaStream_t st, bool with_hz);
+int join_halo_stream(fdtd_ctx *c);
+
+/* the three parts of a step segment (see fdtd_ctx.cu) */
+enum Segment { SEG_FUSED, SEG_H, SEG_E };
+int seg_launch(fdtd_ctx *c, const fdtd::Src &s, Segment seg);
+int seg_exchange(fdtd_ctx *c, Segment seg);
+int seg_finish(fdtd_ctx *c, Segment seg);
+
+/* one context, optionally timed (one process per GPU) */
+int run_impl(fdtd_ctx *c, size_t steps, double *time_counter, float *total_ms, float *h_ms, float *e_ms);
+/* n contexts driven by this thread: n == 1 -> run_impl, n > 1 -> all slabs of a group (fdtd_group.cu) */
+int step_many(fdtd_ctx *const *cs, int n, size_t steps, double *time_counter);
+int exchange_many_for_dump(fdtd_ctx *const *cs, int n);
+
+/* dump pipeline (fdtd_dump.cu) */
+void pipe_destroy(fdtd_ctx *c);
+int propagate_many(fdtd_ctx *const *cs, int n, const fdtd_dump_sink *sinks, size_t *steps_done, double *time_counter);
+
+} /* namespace fdtdi */

@@ -39,7 +39,7 @@
  */
 #pragma once
 
-#include "fdtd_kernels.cuh"
+#include "fdtd_types.cuh"
 
 namespace fdtd {
 

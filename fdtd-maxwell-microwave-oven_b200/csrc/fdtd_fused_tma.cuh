@@ -28,15 +28,9 @@
  */
 #pragma once
 
-#include <cuda.h>
-
-#include "fdtd_kernels.cuh"
+#include "fdtd_types.cuh"
 
 namespace fdtd {
-
-struct TmaMaps {
-    CUtensorMap m[6]; /* ex ey ez hx hy hz of the buffer set being read */
-};
 
 namespace tma {
 
@@ -83,14 +77,6 @@ __device__ __forceinline__ void load_box(void *dst, const CUtensorMap *map, int 
 
 } /* namespace tma */
 
-/* shared-memory footprint of one box, padded so that every box starts on a 128-byte boundary */
-__host__ __device__ inline int tma_box_doubles(int bx, int by)
-{
-    const int n = (bx + 4) * (by + 2);
-    return (n + 15) / 16 * 16;
-}
-
-constexpr int kTmaMaxStages = 8;
 
 /* CWX, CWY: block shape in warps (32*CWX x CWY threads) known at compile time, so that every
  * shared-memory offset is an immediate; 0 = read the shape from blockDim (any launch shape). */

@@ -1,0 +1,294 @@
+/*
+ * fdtd_group.cu -- all z-slabs of a cavity driven by ONE host thread (fdtd_group_*).
+ *
+ * The reference is a single-threaded C program; this keeps its host program one: no MPI, no
+ * launcher.  A group is n slab contexts, one per GPU of the box, with a NCCL communicator made by
+ * ncclCommInitAll.  Every call only queues work; the slabs advance concurrently on their own
+ * streams.  Because one thread issues the NCCL calls of all ranks, each exchange is wrapped in a
+ * single NCCL group (otherwise rank 0's send would wait for a receive this thread has not posted
+ * yet): that is what the three-part segments of fdtd_ctx.cu are for.
+ *
+ * The one-process-per-GPU route (fdtd_ctx_create_slab + fdtd_ctx_comm_init) runs the same segments
+ * without the outer group.
+ */
+#include "fdtd_ctx.hpp"
+
+#include <vector>
+
+using namespace fdtdi;
+
+struct fdtd_group {
+    std::vector<fdtd_ctx *> ctx;
+};
+
+namespace fdtdi {
+
+/* NCCL group around a per-slab call */
+template <typename F>
+int grouped(fdtd_ctx *const *cs, int n, F &&per_slab)
+{
+    if (n > 1)
+        NCCL_TRY(g_nccl.GroupStart());
+    int rc = FDTD_OK;
+    for (int r = 0; r < n && rc == FDTD_OK; ++r)
+        rc = per_slab(cs[r]);
+    if (n > 1) {
+        ncclResult_t e = g_nccl.GroupEnd();
+        if (rc == FDTD_OK && e != ncclSuccess) {
+            fdtd_set_error("ncclGroupEnd: %s", g_nccl.GetErrorString(e));
+            rc = FDTD_E_NCCL;
+        }
+    }
+    return rc;
+}
+
+/* dumps read node plane k1 of Ex, Ey and Hz (main.c:517-520, 538-539) */
+int exchange_many_for_dump(fdtd_ctx *const *cs, int n)
+{
+    if (cs[0]->nranks == 1)
+        return FDTD_OK;
+    for (int r = 0; r < n; ++r) {
+        FDTD_TRY(use_device(cs[r]));
+        cs[r]->e_halo_valid = false;
+        FDTD_TRY(join_halo_stream(cs[r]));
+    }
+    FDTD_TRY(grouped(cs, n, [](fdtd_ctx *c) {
+        FDTD_TRY(use_device(c));
+        return exchange_e(c, c->s_main, true);
+    }));
+    for (int r = 0; r < n; ++r)
+        cs[r]->e_halo_valid = true;
+    return FDTD_OK;
+}
+
+static int group_run(fdtd_ctx *const *cs, int n, size_t steps, double *time_counter)
+{
+    /* kernel choice must be the same on every slab: the halo plans differ */
+    bool want_fused = cs[0]->opt_kernel >= 2;
+    if (want_fused) {
+        bool nomem = false;
+        for (int r = 0; r < n; ++r) {
+            FDTD_TRY(use_device(cs[r]));
+            const int rc = ensure_pong(cs[r]);
+            if (rc == FDTD_E_NOMEM && cs[r]->kernel_auto)
+                nomem = true;
+            else if (rc != FDTD_OK)
+                return rc;
+        }
+        if (nomem) {
+            for (int r = 0; r < n; ++r)
+                fall_back_to_split(cs[r]);
+            want_fused = false;
+        }
+    }
+    /* halos (the flags are identical on all slabs by construction) */
+    fdtd_ctx *c0 = cs[0];
+    const bool need_e = !c0->e_halo_valid;
+    const bool need_h = !c0->h_halo_valid || (want_fused && !c0->low_e_halo_valid);
+    if (need_e || need_h) {
+        for (int r = 0; r < n; ++r) {
+            FDTD_TRY(use_device(cs[r]));
+            FDTD_TRY(join_halo_stream(cs[r]));
+        }
+        FDTD_TRY(grouped(cs, n, [&](fdtd_ctx *c) {
+            FDTD_TRY(use_device(c));
+            if (need_e)
+                FDTD_TRY(exchange_e(c, c->s_main, false));
+            if (need_h)
+                FDTD_TRY(exchange_h(c, c->s_main, want_fused));
+            return (int)FDTD_OK;
+        }));
+        for (int r = 0; r < n; ++r) {
+            cs[r]->e_halo_valid = cs[r]->h_halo_valid = true;
+            cs[r]->low_e_halo_valid = want_fused;
+        }
+    }
+    for (int r = 0; r < n; ++r) { /* the first step's waits need recorded events */
+        FDTD_TRY(use_device(cs[r]));
+        CUDA_TRY(cudaEventRecord(cs[r]->ev_ehalo, cs[r]->s_main));
+        CUDA_TRY(cudaEventRecord(cs[r]->ev_hhalo, cs[r]->s_main));
+    }
+
+    const Segment fused_plan[1] = {SEG_FUSED}, split_plan[2] = {SEG_H, SEG_E};
+    const Segment *plan = want_fused ? fused_plan : split_plan;
+    const int nseg = want_fused ? 1 : 2;
+    double t = *time_counter;
+    for (size_t done = 0; done < steps;) {
+        const size_t chunk = std::min(steps - done, (size_t)kSrcRing);
+        double t_chunk = t;
+        for (int r = 0; r < n; ++r) {
+            t_chunk = t;
+            FDTD_TRY(use_device(cs[r]));
+            FDTD_TRY(stage_source_rows(cs[r], chunk, &t_chunk));
+        }
+        for (size_t s = 0; s < chunk; ++s) {
+            for (int g = 0; g < nseg; ++g) {
+                for (int r = 0; r < n; ++r) {
+                    fdtd_ctx *c = cs[r];
+                    const fdtd::Src src = make_src(c, c->src_dev + s * 2 * (size_t)c->src_n);
+                    FDTD_TRY(seg_launch(c, src, plan[g]));
+                }
+                FDTD_TRY(grouped(cs, n, [&](fdtd_ctx *c) { return seg_exchange(c, plan[g]); }));
+                for (int r = 0; r < n; ++r)
+                    FDTD_TRY(seg_finish(cs[r], plan[g]));
+            }
+        }
+        t = t_chunk;
+        done += chunk;
+    }
+    *time_counter = t;
+    return FDTD_OK;
+}
+
+int step_many(fdtd_ctx *const *cs, int n, size_t steps, double *time_counter)
+{
+    if (n == 1)
+        return run_impl(cs[0], steps, time_counter, nullptr, nullptr, nullptr);
+    return group_run(cs, n, steps, time_counter);
+}
+
+} /* namespace fdtdi */
+
+/* ============================================ C ABI ========================================= */
+
+extern "C" {
+
+int fdtd_group_create(const fdtd_params *p, int ngpus, const int *devices, fdtd_group **out)
+{
+    if (!p || !out || ngpus < 1 || ngpus > 64) {
+        fdtd_set_error("fdtd_group_create: bad argument (ngpus %d)", ngpus);
+        return FDTD_E_ARG;
+    }
+    fdtd_group *g = new (std::nothrow) fdtd_group();
+    if (!g) {
+        fdtd_set_error("fdtd_group_create: out of host memory");
+        return FDTD_E_NOMEM;
+    }
+    std::vector<int> dev(ngpus);
+    for (int r = 0; r < ngpus; ++r)
+        dev[r] = devices ? devices[r] : r;
+    int rc = FDTD_OK;
+    for (int r = 0; r < ngpus && rc == FDTD_OK; ++r) {
+        fdtd_ctx *c = nullptr;
+        rc = create_impl(p, dev[r], r, ngpus, &c);
+        if (rc == FDTD_OK)
+            g->ctx.push_back(c);
+    }
+    if (rc == FDTD_OK && ngpus > 1) {
+        rc = nccl_bind();
+        if (rc == FDTD_OK) {
+            std::vector<ncclComm_t> comms(ngpus);
+            ncclResult_t e = g_nccl.CommInitAll(comms.data(), ngpus, dev.data());
+            if (e != ncclSuccess) {
+                fdtd_set_error("ncclCommInitAll: %s", g_nccl.GetErrorString(e));
+                rc = FDTD_E_NCCL;
+            } else {
+                for (int r = 0; r < ngpus; ++r) {
+                    g->ctx[r]->comm = comms[r];
+                    g->ctx[r]->has_comm = true;
+                }
+            }
+        }
+    }
+    if (rc != FDTD_OK) {
+        for (fdtd_ctx *c : g->ctx)
+            fdtd_ctx_destroy(c);
+        delete g;
+        return rc;
+    }
+    *out = g;
+    return FDTD_OK;
+}
+
+int fdtd_group_destroy(fdtd_group *g)
+{
+    if (!g)
+        return FDTD_OK;
+    for (fdtd_ctx *c : g->ctx)
+        fdtd_ctx_destroy(c);
+    delete g;
+    return FDTD_OK;
+}
+
+int fdtd_group_size(fdtd_group *g)
+{
+    return g ? (int)g->ctx.size() : 0;
+}
+
+int fdtd_group_ctx(fdtd_group *g, int rank, fdtd_ctx **out)
+{
+    if (!g || !out || rank < 0 || rank >= (int)g->ctx.size()) {
+        fdtd_set_error("fdtd_group_ctx: bad argument (rank %d)", rank);
+        return FDTD_E_ARG;
+    }
+    *out = g->ctx[rank];
+    return FDTD_OK;
+}
+
+#define GROUP_CHECK(who)                                                                       \
+    if (!g || g->ctx.empty()) {                                                                \
+        fdtd_set_error(who ": group is NULL");                                                 \
+        return FDTD_E_ARG;                                                                     \
+    }
+
+int fdtd_group_set_option(fdtd_group *g, const char *key, long value)
+{
+    GROUP_CHECK("fdtd_group_set_option");
+    for (fdtd_ctx *c : g->ctx)
+        FDTD_TRY(fdtd_ctx_set_option(c, key, value));
+    return FDTD_OK;
+}
+
+int fdtd_group_upload(fdtd_group *g, const fdtd_fields *whole_cavity)
+{
+    GROUP_CHECK("fdtd_group_upload");
+    for (fdtd_ctx *c : g->ctx)
+        FDTD_TRY(fdtd_upload(c, whole_cavity));
+    return FDTD_OK;
+}
+
+int fdtd_group_download(fdtd_group *g, const fdtd_fields *whole_cavity)
+{
+    GROUP_CHECK("fdtd_group_download");
+    for (fdtd_ctx *c : g->ctx)
+        FDTD_TRY(fdtd_download(c, whole_cavity));
+    return FDTD_OK;
+}
+
+int fdtd_group_set_initial_conditions(fdtd_group *g)
+{
+    GROUP_CHECK("fdtd_group_set_initial_conditions");
+    for (fdtd_ctx *c : g->ctx)
+        FDTD_TRY(fdtd_set_initial_conditions(c));
+    return FDTD_OK;
+}
+
+int fdtd_group_run(fdtd_group *g, size_t steps, double *time_counter)
+{
+    GROUP_CHECK("fdtd_group_run");
+    if (!time_counter) {
+        fdtd_set_error("fdtd_group_run: time_counter is NULL");
+        return FDTD_E_ARG;
+    }
+    for (fdtd_ctx *c : g->ctx)
+        FDTD_TRY(check_ctx(c, "fdtd_group_run"));
+    return step_many(g->ctx.data(), (int)g->ctx.size(), steps, time_counter);
+}
+
+int fdtd_group_sync(fdtd_group *g)
+{
+    GROUP_CHECK("fdtd_group_sync");
+    for (fdtd_ctx *c : g->ctx)
+        FDTD_TRY(fdtd_sync(c));
+    return FDTD_OK;
+}
+
+int fdtd_group_propagate(fdtd_group *g, const fdtd_dump_sink *sinks, size_t *steps_done, double *time_counter)
+{
+    GROUP_CHECK("fdtd_group_propagate");
+    for (fdtd_ctx *c : g->ctx)
+        FDTD_TRY(check_ctx(c, "fdtd_group_propagate"));
+    return propagate_many(g->ctx.data(), (int)g->ctx.size(), sinks, steps_done, time_counter);
+}
+
+} /* extern "C" */

@@ -13,8 +13,10 @@
  * libsilo exists.  As in the reference the directory r/ must already exist;
  * if it does not, the run fails with the reference's message "Could not create DB".
  *
- * Environment: FDTD_B200_DEVICE (CUDA device index, default 0), FDTD_B200_NO_DUMPS=1 (step
- * without writing anything), FDTD_B200_REPORT=1 (timing summary on stderr).
+ * Environment: FDTD_B200_DEVICE (CUDA device index, default 0), FDTD_B200_GPUS=N (split the cavity
+ * into N z-slabs on GPUs 0..N-1 of this box; still one process, one thread: fdtd_group_*; every
+ * slab writes its own brick r/result%04d.slab<r>.raw whose BOV header carries the z origin),
+ * FDTD_B200_NO_DUMPS=1 (step without writing anything), FDTD_B200_REPORT=1 (timing summary on stderr).
  */
 #define _POSIX_C_SOURCE 199309L
 #include "fdtd_b200.h"
@@ -38,6 +40,7 @@ static void fail_lib(const char *what)
 }
 
 typedef struct file_sink {
+    int slab, nslabs;
     FILE *raw;
     char base[128];
     size_t dims[3];
@@ -54,7 +57,10 @@ static int sink_begin(void *user, int iteration, const size_t dims[3], size_t k0
 {
     file_sink *s = (file_sink *)user;
     char name[160];
-    snprintf(s->base, sizeof s->base, "r/result%04d", iteration);
+    if (s->nslabs > 1)
+        snprintf(s->base, sizeof s->base, "r/result%04d.slab%d", iteration, s->slab);
+    else
+        snprintf(s->base, sizeof s->base, "r/result%04d", iteration);
     snprintf(name, sizeof name, "%s.raw", s->base);
     s->raw = fopen(name, "wb");
     if (!s->raw)
@@ -116,14 +122,17 @@ int main(int argc, const char *argv[])
 {
     fdtd_params params;
     fdtd_ctx *ctx = NULL;
-    file_sink files;
-    fdtd_dump_sink sink;
+    fdtd_group *group = NULL;
+    static file_sink files[64];
+    fdtd_dump_sink sinks[64];
     size_t steps = 0;
     double t_end = 0.0, t0, t1;
     const char *dev_env = getenv("FDTD_B200_DEVICE");
+    const char *gpus_env = getenv("FDTD_B200_GPUS");
     const char *no_dumps = getenv("FDTD_B200_NO_DUMPS");
     const char *report = getenv("FDTD_B200_REPORT");
-    int rc;
+    const int ngpus = gpus_env ? atoi(gpus_env) : 1;
+    int rc, r;
 
     printf("Welcome into our microwave oven eletrico-magnetic field simulator! \n");
 
@@ -140,39 +149,58 @@ int main(int argc, const char *argv[])
         fail("The time step must be lower than the simulation time!");
 
     printf("Initializing fields\n");
-    if (fdtd_ctx_create(&params, dev_env ? atoi(dev_env) : 0, &ctx) != FDTD_OK)
+    if (ngpus < 1 || ngpus > 64) {
+        fprintf(stderr, "FDTD_B200_GPUS must be between 1 and 64\n");
+        return EXIT_FAILURE;
+    }
+    if (ngpus > 1) {
+        if (fdtd_group_create(&params, ngpus, NULL, &group) != FDTD_OK)
+            fail_lib("initialize_fields");
+    } else if (fdtd_ctx_create(&params, dev_env ? atoi(dev_env) : 0, &ctx) != FDTD_OK) {
         fail_lib("initialize_fields");
+    }
     if (params.mode == 0)
         printf("Validation mode activated. \n");
 
     printf("Creating mesh\n");
 
     printf("Setting initial conditions\n");
-    if (params.mode == 0 && fdtd_set_initial_conditions(ctx) != FDTD_OK)
+    if (params.mode == 0 &&
+        (group ? fdtd_group_set_initial_conditions(group) : fdtd_set_initial_conditions(ctx)) != FDTD_OK)
         fail_lib("set_initial_conditions");
 
     printf("Launching simulation\n");
     fflush(stdout);
-    memset(&files, 0, sizeof files);
-    files.dx = params.spatial_step;
-    sink.user = &files;
-    sink.begin = sink_begin;
-    sink.variable = sink_variable;
-    sink.end = sink_end;
+    memset(files, 0, sizeof files);
+    for (r = 0; r < ngpus; ++r) {
+        files[r].slab = r;
+        files[r].nslabs = ngpus;
+        files[r].dx = params.spatial_step;
+        sinks[r].user = &files[r];
+        sinks[r].begin = sink_begin;
+        sinks[r].variable = sink_variable;
+        sinks[r].end = sink_end;
+    }
     t0 = now_s();
-    rc = fdtd_propagate(ctx, (no_dumps && no_dumps[0] == '1') ? NULL : &sink, &steps, &t_end);
+    if (group)
+        rc = fdtd_group_propagate(group, (no_dumps && no_dumps[0] == '1') ? NULL : sinks, &steps, &t_end);
+    else
+        rc = fdtd_propagate(ctx, (no_dumps && no_dumps[0] == '1') ? NULL : &sinks[0], &steps, &t_end);
     t1 = now_s();
     if (rc == FDTD_E_IO)
         fail("Could not create DB\n"); /* main.c:556-559 */
     if (rc != FDTD_OK)
         fail_lib("propagate_fields");
     if (report && report[0] == '1')
-        fprintf(stderr, "[fdtd_b200] %zu x %zu x %zu cells, %zu steps in %.3f s: %.3f Gcell-updates/s\n",
-                params.maxi, params.maxj, params.maxk, steps, t1 - t0,
+        fprintf(stderr, "[fdtd_b200] %zu x %zu x %zu cells on %d GPU(s), %zu steps in %.3f s: %.3f Gcell-updates/s\n",
+                params.maxi, params.maxj, params.maxk, ngpus, steps, t1 - t0,
                 1e-9 * (double)params.maxi * (double)params.maxj * (double)params.maxk * (double)steps / (t1 - t0));
 
     printf("Freeing memory...\n");
-    fdtd_ctx_destroy(ctx);
+    if (group)
+        fdtd_group_destroy(group);
+    else
+        fdtd_ctx_destroy(ctx);
 
     printf("Simulation complete!\n");
     return 0;

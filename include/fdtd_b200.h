@@ -175,6 +175,28 @@ int fdtd_propagate(fdtd_ctx *ctx, const fdtd_dump_sink *sink, size_t *steps_done
 int fdtd_host_alloc(size_t bytes, void **out);
 int fdtd_host_free(void *ptr);
 
+/* ---- all slabs of a cavity from ONE host thread ------------------------------------------------
+ * The reference is a single-threaded C program (main.c:807-853); a group keeps its multi-GPU host
+ * program one: n z-slab contexts, one per GPU of the box, wired with ncclCommInitAll -- no MPI, no
+ * launcher.  Every call queues work on all slabs; they advance concurrently.  The per-slab contexts
+ * stay accessible (fdtd_group_ctx) for fdtd_upload_slab, fdtd_aggregate, fdtd_checksum and so on.
+ * devices: ngpus CUDA device indices, or NULL for 0 .. ngpus-1. */
+typedef struct fdtd_group fdtd_group;
+int fdtd_group_create(const fdtd_params *p, int ngpus, const int *devices, fdtd_group **out);
+int fdtd_group_destroy(fdtd_group *group);
+int fdtd_group_size(fdtd_group *group);
+int fdtd_group_ctx(fdtd_group *group, int rank, fdtd_ctx **out);
+int fdtd_group_set_option(fdtd_group *group, const char *key, long value);
+int fdtd_group_upload(fdtd_group *group, const fdtd_fields *whole_cavity);      /* each slab takes its planes */
+int fdtd_group_download(fdtd_group *group, const fdtd_fields *whole_cavity);
+int fdtd_group_set_initial_conditions(fdtd_group *group);                        /* main.c:416-424 */
+int fdtd_group_run(fdtd_group *group, size_t steps, double *time_counter);      /* loop body main.c:770-779 */
+int fdtd_group_sync(fdtd_group *group);
+/* propagate_fields(), main.c:755-799; sinks: one per slab (ngpus entries; each is called from its own
+ * writer thread with that slab's planes and k0), or NULL for no dumps. */
+int fdtd_group_propagate(fdtd_group *group, const fdtd_dump_sink *sinks, size_t *steps_done,
+                         double *time_counter);
+
 /* Diagnostics that sit next to the path in the reference (they never feed back into the fields).
  * Both are reductions and agree with the reference's sequential sums to rounding, not bit for bit.
  * A slab context returns its own zones' contribution; add the slabs up for the cavity.

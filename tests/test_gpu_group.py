@@ -1,0 +1,111 @@
+"""All slabs from ONE process and ONE thread (fdtd_group_*, ncclCommInitAll): same results as the
+single-domain oracle, bit for bit -- stepping, dumps, and the C host program with FDTD_B200_GPUS."""
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, bits_equal, to_oracle_params, upper
+
+pytestmark = pytest.mark.gpu
+EXE = os.path.join(ROOT, "fdtd-maxwell-microwave-oven_b200", "microwave")
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def ngpu():
+    return torch.cuda.device_count()
+
+
+VARIANTS = [dict(kernel=3, strip=2, kchunk=4, warps_x=2, warps_y=2, stages=3),
+            dict(kernel=2, strip=1, kchunk=32, warps_x=1, warps_y=4),
+            dict(kernel=1, strip=2, kchunk=3, warps_x=2, warps_y=2),
+            dict(kernel=0)]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("mode", [0, 1])
+def test_group_run_matches_oracle(F, oracle, variant, mode):
+    if ngpu() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    o = oracle.restatement()
+    for world in sorted({2, min(ngpu(), 4), min(ngpu(), 8)}):
+        dims = (37, 28, 23)
+        args = tuple((d + .5) * 1e-3 for d in dims) + (0.001, 6e-13, 1.2e-10, 2, mode)
+        p, q = F.make_params(*args), oracle.make_params(*args)
+        assert p.dims() == dims
+        f = oracle.alloc_fields(*dims, rng=np.random.default_rng(17))
+        with F.Group(p, world) as g:
+            for k, v in variant.items():
+                g.set_option(k, v)
+            g.upload(upper(f))
+            t = g.run(4, 0.0)
+            t = g.run(3, t)
+            t_cpu = o.run(q, f, 7)
+            assert t == t_cpu
+            got = g.download()
+            for k, want in f.items():
+                assert bits_equal(got[k[0].upper() + k[1:]], want), (world, k)
+            sums = [s.checksum() for s in g.slabs]
+            total = [sum(s[a] for s in sums) % (1 << 64) for a in range(6)]
+            assert total == F.checksum_host(upper(f))
+            for v in range(6):
+                whole = np.concatenate([s.aggregate(v) for s in g.slabs], axis=0)
+                assert bits_equal(whole, o.aggregate(q, f, v)), (world, v)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_group_propagate_matches_reference_dumps(F, golden, tmp_path, mode):
+    if ngpu() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    g_ = golden["propagate_tiny"][f"mode{mode}"]
+    path = tmp_path / "p.txt"
+    path.write_text("\n".join(g_["params"]))
+    p = F.load_parameters(path)
+    nx, ny, nz = p.dims()
+    logs = {}
+    with F.Group(p, 2) as g:
+        if mode == 0:
+            g.set_initial_conditions()
+        steps, _ = g.propagate(
+            on_begin=lambda r, it, dims, k0: logs.setdefault(it, {}).setdefault(r, {"k0": k0, "dims": dims, "vars": {}}),
+            on_variable=lambda r, name, arr: logs[max(i for i in logs if r in logs[i])][r]["vars"].__setitem__(name, arr))
+        assert steps == g_["steps"]
+        out = g.download()
+    its = sorted(logs)
+    assert ["r/result%04d.silo" % i for i in its] == [d["file"] for d in g_["dumps"]]
+    for it, want in zip(its, g_["dumps"]):
+        slabs = [logs[it][r] for r in sorted(logs[it])]
+        assert [s["k0"] for s in slabs] == [g.slabs[r].k0 for r in range(2)]
+        for name, dig in want["vars"].items():
+            whole = np.concatenate([s["vars"][name] for s in slabs])
+            assert whole.size == nx * ny * nz and digest(whole) == dig, (it, name)
+    for k, want in g_["final_sha256"].items():
+        assert digest(out[k[0].upper() + k[1:]]) == want, k
+
+
+def test_microwave_with_two_gpus(F, golden, tmp_path):
+    """FDTD_B200_GPUS=2 ./microwave params.txt : one process, two slabs, bricks that add up."""
+    if ngpu() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    g_ = golden["propagate_tiny"]["mode1"]
+    (tmp_path / "params.txt").write_text("\n".join(g_["params"]))
+    (tmp_path / "r").mkdir()
+    r = subprocess.run([EXE, "params.txt"], cwd=tmp_path, capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, FDTD_B200_GPUS="2"))
+    assert r.returncode == 0, r.stderr
+    nx, ny, nz = g_["grid"]
+    k = [F.slab_range(nz, rr, 2) for rr in range(2)]
+    names = ["ex", "ey", "ez", "hx", "hy", "hz"]
+    for d in g_["dumps"]:
+        base = os.path.basename(d["file"]).replace(".silo", "")
+        parts = [np.fromfile(tmp_path / "r" / f"{base}.slab{rr}.raw") for rr in range(2)]
+        for v, name in enumerate(names):
+            whole = np.concatenate([parts[rr][v * nx * ny * (k[rr][1] - k[rr][0]):(v + 1) * nx * ny * (k[rr][1] - k[rr][0])]
+                                    for rr in range(2)])
+            assert digest(whole) == d["vars"][name], (base, name)
