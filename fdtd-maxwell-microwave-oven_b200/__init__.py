@@ -108,6 +108,8 @@ SIGNATURES = {
     "fdtd_group_set_initial_conditions": (C.c_int, [C.c_void_p]),
     "fdtd_group_run": (C.c_int, [C.c_void_p, C.c_size_t, _D]),
     "fdtd_group_sync": (C.c_int, [C.c_void_p]),
+    "fdtd_group_aggregate": (C.c_int, [C.c_void_p, C.c_int, _D]),
+    "fdtd_group_energy": (C.c_int, [C.c_void_p, C.c_int, _D, _D]),
     "fdtd_group_propagate": (C.c_int, [C.c_void_p, C.POINTER(DumpSink), C.POINTER(C.c_size_t), _D]),
     "fdtd_energy": (C.c_int, [_CTX, C.c_int, _D, _D]),
     "fdtd_validation_error": (C.c_int, [_CTX, C.c_double, _D, _D]),
@@ -447,6 +449,17 @@ class Group:
 
     def sync(self):
         _check(lib.fdtd_group_sync(self._g))
+
+    def aggregate(self, var):
+        nx, ny, nz = self.p.dims()
+        out = np.empty((nz, ny, nx))
+        _check(lib.fdtd_group_aggregate(self._g, int(var), out.ctypes.data_as(_D)))
+        return out
+
+    def energy(self, as_coded=False):
+        e, h = C.c_double(), C.c_double()
+        _check(lib.fdtd_group_energy(self._g, 1 if as_coded else 0, C.byref(e), C.byref(h)))
+        return e.value, h.value
 
     def propagate(self, on_begin=None, on_variable=None, on_end=None, dumps=True):
         """callbacks get the slab rank as first argument; they run on per-slab writer threads"""

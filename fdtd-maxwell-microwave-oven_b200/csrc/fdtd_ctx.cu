@@ -64,6 +64,16 @@ int check_ctx(const fdtd_ctx *c, const char *who)
     return FDTD_OK;
 }
 
+int check_solo(const fdtd_ctx *c, const char *who)
+{
+    FDTD_TRY(check_ctx(c, who));
+    if (c->in_group && c->nranks > 1) {
+        fdtd_set_error("%s: this context is a slab of an fdtd_group; use the fdtd_group_* call", who);
+        return FDTD_E_STATE;
+    }
+    return FDTD_OK;
+}
+
 int use_device(const fdtd_ctx *c)
 {
     CUDA_TRY(cudaSetDevice(c->device));
@@ -332,11 +342,16 @@ int launch_fused_tma_t(fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cuda
         fdtd_set_error("TMA ring of %d stages x %d x %d tile needs %zu bytes of shared memory", stages, bx, by, smem);
         return FDTD_E_ARG;
     }
-    static bool configured = false; /* one flag per instantiation */
+    /* the opt-in to more than 48 KB of dynamic shared memory is per device: remember it per context */
+    const void *fn = (const void *)k_step_fused_tma<TY, CWX, CWY>;
+    bool configured = false;
+    for (int k = 0; k < c->n_smem_optin; ++k)
+        configured = configured || c->smem_optin[k] == fn;
     if (!configured) {
         CUDA_TRY(cudaFuncSetAttribute(k_step_fused_tma<TY, CWX, CWY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       226 * 1024));
-        configured = true;
+        if (c->n_smem_optin < 16)
+            c->smem_optin[c->n_smem_optin++] = fn;
     }
     Span sp{kl_begin, kl_end, (int)std::max(c->opt_kchunk, 2L), 0};
     dim3 block(bx, wy);
@@ -1088,7 +1103,7 @@ int fdtd_set_initial_conditions(fdtd_ctx *c)
 
 int fdtd_set_source(fdtd_ctx *c, double t)
 {
-    FDTD_TRY(check_ctx(c, "fdtd_set_source"));
+    FDTD_TRY(check_solo(c, "fdtd_set_source"));
     FDTD_TRY(use_device(c));
     if (c->p.mode != 1 || c->src_n == 0) {
         fdtd_set_error("fdtd_set_source: context has no source (validation mode)");
@@ -1110,7 +1125,7 @@ int fdtd_set_source(fdtd_ctx *c, double t)
 
 int fdtd_update_H_field(fdtd_ctx *c)
 {
-    FDTD_TRY(check_ctx(c, "fdtd_update_H_field"));
+    FDTD_TRY(check_solo(c, "fdtd_update_H_field"));
     FDTD_TRY(use_device(c));
     FDTD_TRY(refresh_halos(c));
     launch_h(c, no_src(), 1, c->g.nk + c->g.top + 1, c->s_main);
@@ -1121,7 +1136,7 @@ int fdtd_update_H_field(fdtd_ctx *c)
 
 int fdtd_update_E_field(fdtd_ctx *c)
 {
-    FDTD_TRY(check_ctx(c, "fdtd_update_E_field"));
+    FDTD_TRY(check_solo(c, "fdtd_update_E_field"));
     FDTD_TRY(use_device(c));
     FDTD_TRY(refresh_halos(c));
     launch_e(c, no_src(), 1, c->g.nk + 1, c->s_main);
@@ -1132,7 +1147,7 @@ int fdtd_update_E_field(fdtd_ctx *c)
 
 int fdtd_run(fdtd_ctx *c, size_t steps, double *time_counter)
 {
-    FDTD_TRY(check_ctx(c, "fdtd_run"));
+    FDTD_TRY(check_solo(c, "fdtd_run"));
     if (!time_counter) {
         fdtd_set_error("fdtd_run: time_counter is NULL");
         return FDTD_E_ARG;
@@ -1142,7 +1157,7 @@ int fdtd_run(fdtd_ctx *c, size_t steps, double *time_counter)
 
 int fdtd_run_timed(fdtd_ctx *c, size_t steps, double *time_counter, float *total_ms, float *h_ms, float *e_ms)
 {
-    FDTD_TRY(check_ctx(c, "fdtd_run_timed"));
+    FDTD_TRY(check_solo(c, "fdtd_run_timed"));
     if (!time_counter || !total_ms) {
         fdtd_set_error("fdtd_run_timed: NULL argument");
         return FDTD_E_ARG;

@@ -90,6 +90,7 @@ struct fdtd_ctx {
     bool low_e_halo_valid; /* fused step only: plane 0 also holds the lower neighbour's Ex, Ey, Ez */
     ncclComm_t comm;
     bool has_comm;
+    bool in_group;      /* slab of an fdtd_group: calls that exchange halos go through the group */
 
     /* source */
     fdtd_source_plan plan;
@@ -107,6 +108,8 @@ struct fdtd_ctx {
     TmaMaps tma_maps[2];
     double *tma_base[2];
     int tma_bx, tma_by;
+    const void *smem_optin[16]; /* kernels already opted in to large dynamic shared memory on this device */
+    int n_smem_optin;
     mutable long launches; /* kernels of this library launched so far (reports) */
     int launch_error;      /* first failure inside a launch helper, reported by queue_step */
     bool kernel_auto;      /* "kernel" was not chosen by the caller: may fall back to the split kernels */
@@ -122,6 +125,9 @@ struct fdtd_ctx {
 namespace fdtdi {
 
 int check_ctx(const fdtd_ctx *c, const char *who);
+/* check_ctx + refuse slabs of a group: a call that exchanges halos must be issued for all slabs
+ * inside one NCCL group, which only the fdtd_group_* entry points do */
+int check_solo(const fdtd_ctx *c, const char *who);
 int use_device(const fdtd_ctx *c);
 double *field_ptr(const fdtd_ctx *c, int idx);
 
@@ -154,6 +160,9 @@ int run_impl(fdtd_ctx *c, size_t steps, double *time_counter, float *total_ms, f
 /* n contexts driven by this thread: n == 1 -> run_impl, n > 1 -> all slabs of a group (fdtd_group.cu) */
 int step_many(fdtd_ctx *const *cs, int n, size_t steps, double *time_counter);
 int exchange_many_for_dump(fdtd_ctx *const *cs, int n);
+
+int aggregate_many(fdtd_ctx *const *cs, int n, int var, double *const *host_out);
+int energy_many(fdtd_ctx *const *cs, int n, int as_coded, double *e_energy, double *h_energy);
 
 /* dump pipeline (fdtd_dump.cu) */
 void pipe_destroy(fdtd_ctx *c);

@@ -7,36 +7,61 @@
 
 using namespace fdtdi;
 
+namespace fdtdi {
+
+/* fdtd_energy over the n slabs this thread drives (n = 1: one context); the slabs' sums add up */
+int energy_many(fdtd_ctx *const *cs, int n, int as_coded, double *e_energy, double *h_energy)
+{
+    /* the top zone plane of a slab averages with node plane k1 of Ex, Ey, Hz */
+    FDTD_TRY(exchange_many_for_dump(cs, n));
+    double tot[6] = {0, 0, 0, 0, 0, 0};
+    std::vector<double *> dev(n, nullptr);
+    std::vector<double> host(6 * (size_t)n, 0.0);
+    int rc = FDTD_OK;
+    for (int r = 0; r < n && rc == FDTD_OK; ++r) {
+        fdtd_ctx *c = cs[r];
+        rc = use_device(c);
+        if (rc != FDTD_OK)
+            break;
+        if (cudaMalloc((void **)&dev[r], 6 * sizeof(double)) != cudaSuccess) {
+            fdtd_set_error("fdtd_energy: cudaMalloc failed");
+            rc = FDTD_E_CUDA;
+            break;
+        }
+        cudaMemsetAsync(dev[r], 0, 6 * sizeof(double), c->s_main);
+        dim3 block(64, 4);
+        dim3 grid((c->g.I + 63) / 64, (c->g.J + 3) / 4, c->g.nk);
+        k_energy<<<grid, block, 0, c->s_main>>>(c->g, c->f, as_coded, dev[r]);
+        cudaMemcpyAsync(&host[6 * (size_t)r], dev[r], 6 * sizeof(double), cudaMemcpyDeviceToHost, c->s_main);
+    }
+    for (int r = 0; r < n; ++r) {
+        if (!dev[r])
+            continue;
+        cudaSetDevice(cs[r]->device);
+        if (cudaStreamSynchronize(cs[r]->s_main) != cudaSuccess && rc == FDTD_OK) {
+            fdtd_set_error("fdtd_energy: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = FDTD_E_CUDA;
+        }
+        cudaFree(dev[r]);
+        for (int v = 0; v < 6; ++v)
+            tot[v] += host[6 * (size_t)r + v];
+    }
+    if (rc != FDTD_OK)
+        return rc;
+    const double dv = pow(cs[0]->p.spatial_step, 3); /* main.c:613 */
+    if (e_energy) *e_energy = (tot[0] * dv + tot[1] * dv + tot[2] * dv) * FDTD_EPSILON / 2.; /* main.c:631 */
+    if (h_energy) *h_energy = (tot[3] * dv + tot[4] * dv + tot[5] * dv) * FDTD_MU / 2.;      /* main.c:665 */
+    return FDTD_OK;
+}
+
+} /* namespace fdtdi */
+
 extern "C" {
 
 int fdtd_energy(fdtd_ctx *c, int as_coded, double *e_energy, double *h_energy)
 {
-    FDTD_TRY(check_ctx(c, "fdtd_energy"));
-    FDTD_TRY(use_device(c));
-    if (c->nranks > 1) { /* the top zone plane averages with node plane k1 of Ex, Ey, Hz */
-        FDTD_TRY(join_halo_stream(c));
-        FDTD_TRY(exchange_e(c, c->s_main, true));
-        c->e_halo_valid = true;
-    }
-    double *dev = nullptr;
-    CUDA_TRY(cudaMalloc((void **)&dev, 6 * sizeof(double)));
-    cudaMemsetAsync(dev, 0, 6 * sizeof(double), c->s_main);
-    dim3 block(64, 4);
-    dim3 grid((c->g.I + 63) / 64, (c->g.J + 3) / 4, c->g.nk);
-    k_energy<<<grid, block, 0, c->s_main>>>(c->g, c->f, as_coded, dev);
-    double s[6];
-    cudaError_t e = cudaMemcpyAsync(s, dev, sizeof s, cudaMemcpyDeviceToHost, c->s_main);
-    if (e == cudaSuccess)
-        e = cudaStreamSynchronize(c->s_main);
-    cudaFree(dev);
-    if (e != cudaSuccess) {
-        fdtd_set_error("fdtd_energy: %s", cudaGetErrorString(e));
-        return FDTD_E_CUDA;
-    }
-    const double dv = pow(c->p.spatial_step, 3); /* main.c:613 */
-    if (e_energy) *e_energy = (s[0] * dv + s[1] * dv + s[2] * dv) * FDTD_EPSILON / 2.; /* main.c:631 */
-    if (h_energy) *h_energy = (s[3] * dv + s[4] * dv + s[5] * dv) * FDTD_MU / 2.;      /* main.c:665 */
-    return FDTD_OK;
+    FDTD_TRY(check_solo(c, "fdtd_energy"));
+    return energy_many(&c, 1, as_coded, e_energy, h_energy);
 }
 
 int fdtd_validation_error(fdtd_ctx *c, double t, double sums[6], double rel_l2[3])

@@ -235,6 +235,44 @@ int post_dump_many(fdtd_ctx *const *cs, int n, int iteration, double t_validatio
     return FDTD_OK;
 }
 
+/* fdtd_aggregate for the n slabs this thread drives: host_out[r] receives slab r's zones */
+int aggregate_many(fdtd_ctx *const *cs, int n, int var, double *const *host_out)
+{
+    if (var < 0 || var > 5) {
+        fdtd_set_error("fdtd_aggregate: bad variable index %d", var);
+        return FDTD_E_ARG;
+    }
+    for (int r = 0; r < n; ++r) {
+        fdtd_ctx *c = cs[r];
+        FDTD_TRY(use_device(c));
+        const size_t cnt = (size_t)c->g.I * c->g.J * c->g.nk;
+        if (c->agg_elems < cnt) {
+            if (c->agg_dev) cudaFree(c->agg_dev);
+            c->agg_dev = nullptr;
+            c->agg_elems = 0;
+            CUDA_TRY(cudaMalloc((void **)&c->agg_dev, cnt * sizeof(double)));
+            c->agg_elems = cnt;
+        }
+    }
+    /* zone plane k1-1 of ex, ey, hz reads node plane k1 (main.c:517-520, 538-539) */
+    FDTD_TRY(exchange_many_for_dump(cs, n));
+    for (int r = 0; r < n; ++r) {
+        fdtd_ctx *c = cs[r];
+        FDTD_TRY(use_device(c));
+        const size_t cnt = (size_t)c->g.I * c->g.J * c->g.nk;
+        dim3 block(64, 4);
+        dim3 grid((c->g.I + 63) / 64, (c->g.J + 3) / 4, c->g.nk);
+        k_aggregate<<<grid, block, 0, c->s_main>>>(c->g, field_ptr(c, var), var, c->agg_dev);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(host_out[r], c->agg_dev, cnt * sizeof(double), cudaMemcpyDeviceToHost, c->s_main));
+    }
+    for (int r = 0; r < n; ++r) {
+        FDTD_TRY(use_device(cs[r]));
+        CUDA_TRY(cudaStreamSynchronize(cs[r]->s_main));
+    }
+    return FDTD_OK;
+}
+
 /* propagate_fields(), main.c:755-799, for the n slabs this thread drives (n = 1: one context) */
 int propagate_many(fdtd_ctx *const *cs, int n, const fdtd_dump_sink *sinks, size_t *steps_done, double *time_counter)
 {
@@ -322,39 +360,17 @@ extern "C" {
 
 int fdtd_aggregate(fdtd_ctx *c, int var, double *host_out)
 {
-    FDTD_TRY(check_ctx(c, "fdtd_aggregate"));
-    if (var < 0 || var > 5 || !host_out) {
-        fdtd_set_error("fdtd_aggregate: bad argument (var %d)", var);
+    FDTD_TRY(check_solo(c, "fdtd_aggregate"));
+    if (!host_out) {
+        fdtd_set_error("fdtd_aggregate: host_out is NULL");
         return FDTD_E_ARG;
     }
-    FDTD_TRY(use_device(c));
-    const size_t n = (size_t)c->g.I * c->g.J * c->g.nk;
-    if (c->agg_elems < n) {
-        if (c->agg_dev) cudaFree(c->agg_dev);
-        c->agg_dev = nullptr;
-        c->agg_elems = 0;
-        CUDA_TRY(cudaMalloc((void **)&c->agg_dev, n * sizeof(double)));
-        c->agg_elems = n;
-    }
-    if (c->nranks > 1) {
-        /* zone plane k1-1 of ex, ey, hz reads node plane k1 (main.c:517-520, 538-539) */
-        c->e_halo_valid = false;
-        FDTD_TRY(join_halo_stream(c));
-        FDTD_TRY(exchange_e(c, c->s_main, true));
-        c->e_halo_valid = true;
-    }
-    dim3 block(64, 4);
-    dim3 grid((c->g.I + 63) / 64, (c->g.J + 3) / 4, c->g.nk);
-    k_aggregate<<<grid, block, 0, c->s_main>>>(c->g, field_ptr(c, var), var, c->agg_dev);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(host_out, c->agg_dev, n * sizeof(double), cudaMemcpyDeviceToHost, c->s_main));
-    CUDA_TRY(cudaStreamSynchronize(c->s_main));
-    return FDTD_OK;
+    return aggregate_many(&c, 1, var, &host_out);
 }
 
 int fdtd_propagate(fdtd_ctx *c, const fdtd_dump_sink *sink, size_t *steps_done, double *time_counter)
 {
-    FDTD_TRY(check_ctx(c, "fdtd_propagate"));
+    FDTD_TRY(check_solo(c, "fdtd_propagate"));
     FDTD_TRY(use_device(c));
     return propagate_many(&c, 1, sink, steps_done, time_counter);
 }

@@ -186,6 +186,7 @@ int fdtd_group_create(const fdtd_params *p, int ngpus, const int *devices, fdtd_
                 for (int r = 0; r < ngpus; ++r) {
                     g->ctx[r]->comm = comms[r];
                     g->ctx[r]->has_comm = true;
+                    g->ctx[r]->in_group = true;
                 }
             }
         }
@@ -273,6 +274,27 @@ int fdtd_group_run(fdtd_group *g, size_t steps, double *time_counter)
     for (fdtd_ctx *c : g->ctx)
         FDTD_TRY(check_ctx(c, "fdtd_group_run"));
     return step_many(g->ctx.data(), (int)g->ctx.size(), steps, time_counter);
+}
+
+/* fdtd_aggregate for the whole cavity: host_out has maxi*maxj*maxk doubles (main.c:511-540) */
+int fdtd_group_aggregate(fdtd_group *g, int var, double *host_out)
+{
+    GROUP_CHECK("fdtd_group_aggregate");
+    if (!host_out) {
+        fdtd_set_error("fdtd_group_aggregate: host_out is NULL");
+        return FDTD_E_ARG;
+    }
+    std::vector<double *> out(g->ctx.size());
+    for (size_t r = 0; r < g->ctx.size(); ++r)
+        out[r] = host_out + g->ctx[r]->k0 * (size_t)g->ctx[r]->g.I * (size_t)g->ctx[r]->g.J;
+    return aggregate_many(g->ctx.data(), (int)g->ctx.size(), var, out.data());
+}
+
+/* fdtd_energy summed over the slabs (main.c:602-668) */
+int fdtd_group_energy(fdtd_group *g, int as_coded, double *e_energy, double *h_energy)
+{
+    GROUP_CHECK("fdtd_group_energy");
+    return energy_many(g->ctx.data(), (int)g->ctx.size(), as_coded, e_energy, h_energy);
 }
 
 int fdtd_group_sync(fdtd_group *g)

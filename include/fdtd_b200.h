@@ -179,7 +179,11 @@ int fdtd_host_free(void *ptr);
  * The reference is a single-threaded C program (main.c:807-853); a group keeps its multi-GPU host
  * program one: n z-slab contexts, one per GPU of the box, wired with ncclCommInitAll -- no MPI, no
  * launcher.  Every call queues work on all slabs; they advance concurrently.  The per-slab contexts
- * stay accessible (fdtd_group_ctx) for fdtd_upload_slab, fdtd_aggregate, fdtd_checksum and so on.
+ * stay accessible (fdtd_group_ctx) for calls that touch one slab only (fdtd_upload_slab,
+ * fdtd_download_slab, fdtd_checksum, fdtd_validation_error, fdtd_ctx_info); calls that exchange halos
+ * (stepping, fdtd_aggregate, fdtd_energy, fdtd_propagate) must go through the group, because one
+ * thread has to post every slab's sends and receives inside one NCCL group -- on a slab of a group
+ * they return FDTD_E_STATE.
  * devices: ngpus CUDA device indices, or NULL for 0 .. ngpus-1. */
 typedef struct fdtd_group fdtd_group;
 int fdtd_group_create(const fdtd_params *p, int ngpus, const int *devices, fdtd_group **out);
@@ -192,6 +196,8 @@ int fdtd_group_download(fdtd_group *group, const fdtd_fields *whole_cavity);
 int fdtd_group_set_initial_conditions(fdtd_group *group);                        /* main.c:416-424 */
 int fdtd_group_run(fdtd_group *group, size_t steps, double *time_counter);      /* loop body main.c:770-779 */
 int fdtd_group_sync(fdtd_group *group);
+int fdtd_group_aggregate(fdtd_group *group, int var, double *host_out /* maxi*maxj*maxk */); /* main.c:511-540 */
+int fdtd_group_energy(fdtd_group *group, int as_coded, double *e_energy, double *h_energy); /* main.c:602-668 */
 /* propagate_fields(), main.c:755-799; sinks: one per slab (ngpus entries; each is called from its own
  * writer thread with that slab's planes and k0), or NULL for no dumps. */
 int fdtd_group_propagate(fdtd_group *group, const fdtd_dump_sink *sinks, size_t *steps_done,

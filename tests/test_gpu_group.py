@@ -55,8 +55,13 @@ def test_group_run_matches_oracle(F, oracle, variant, mode):
             total = [sum(s[a] for s in sums) % (1 << 64) for a in range(6)]
             assert total == F.checksum_host(upper(f))
             for v in range(6):
-                whole = np.concatenate([s.aggregate(v) for s in g.slabs], axis=0)
-                assert bits_equal(whole, o.aggregate(q, f, v)), (world, v)
+                assert bits_equal(g.aggregate(v), o.aggregate(q, f, v)), (world, v)
+            e_ref, h_ref = o.energy(q, f)
+            e_gpu, h_gpu = g.energy(as_coded=True)
+            assert abs(e_gpu - e_ref) <= 1e-12 * abs(e_ref) and abs(h_gpu - h_ref) <= 1e-12 * abs(h_ref)
+            with pytest.raises(F.FdtdError) as err:      # a slab of a group cannot exchange halos on its own
+                g.slabs[0].aggregate(0)
+            assert err.value.code == -6
 
 
 @pytest.mark.parametrize("mode", [0, 1])
