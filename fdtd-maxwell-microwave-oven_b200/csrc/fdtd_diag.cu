@@ -12,6 +12,11 @@ namespace fdtdi {
 /* fdtd_energy over the n slabs this thread drives (n = 1: one context); the slabs' sums add up */
 int energy_many(fdtd_ctx *const *cs, int n, int as_coded, double *e_energy, double *h_energy)
 {
+    if (as_coded && cs[0]->nranks > 1) {
+        /* main.c:627 reads Ez at Hz's offsets, i.e. from other planes -- possibly another slab's */
+        fdtd_set_error("fdtd_energy: as_coded is only available on a single-GPU context");
+        return FDTD_E_ARG;
+    }
     /* the top zone plane of a slab averages with node plane k1 of Ex, Ey, Hz */
     FDTD_TRY(exchange_many_for_dump(cs, n));
     double tot[6] = {0, 0, 0, 0, 0, 0};

@@ -208,7 +208,8 @@ int fdtd_group_propagate(fdtd_group *group, const fdtd_dump_sink *sinks, size_t 
  * A slab context returns its own zones' contribution; add the slabs up for the cavity.
  *
  * fdtd_energy: calculate_E_energy() / calculate_H_energy(), main.c:602-668.  as_coded != 0 keeps the
- *   reference's indexing of Ez with Hz's strides (main.c:627); 0 uses the intended zone average.
+ *   reference's indexing of Ez with Hz's strides (main.c:627; single-GPU contexts only, the slip reaches
+ *   across planes); 0 uses the intended zone average.
  * fdtd_validation_error: against the analytic TE101 fields of update_validation_fields_then_subfdtd(),
  *   main.c:670-710, at time_counter: sums[] = {sum (a-Ey)^2, sum a^2, same for Hx, same for Hz};
  *   rel_l2[] = sqrt(num/den) per field (the report's e_r, description.pdf eq. 2).  Either may be NULL. */
