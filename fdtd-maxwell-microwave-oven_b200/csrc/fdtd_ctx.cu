@@ -1082,16 +1082,18 @@ int fdtd_set_initial_conditions(fdtd_ctx *c)
 {
     FDTD_TRY(check_ctx(c, "fdtd_set_initial_conditions"));
     FDTD_TRY(use_device(c));
-    /* glibc sin on the host, like the reference (main.c:422-423), then one upload of Ey */
+    /* glibc sin on the host, like the reference (main.c:422-423), for the planes this slab owns,
+     * then one upload of Ey */
     const DenseShape s = dense_shape(c->p, 1);
-    double *ey = (double *)malloc(s.w * s.h * s.d * sizeof(double));
+    const size_t nplanes = (size_t)c->g.nk + (c->g.top ? 1 : 0);
+    double *ey = (double *)malloc(s.w * s.h * nplanes * sizeof(double));
     if (!ey) {
         fdtd_set_error("fdtd_set_initial_conditions: out of host memory");
         return FDTD_E_NOMEM;
     }
-    int rc = fdtd_initial_conditions_host(&c->p, ey);
+    int rc = fdtd_initial_conditions_planes(&c->p, c->k0, nplanes, ey);
     if (rc == FDTD_OK)
-        rc = copy_field(c, 1, ey + slab_offset(c, 1, true), true);
+        rc = copy_field(c, 1, ey, true);
     if (rc == FDTD_OK && cudaStreamSynchronize(c->s_main) != cudaSuccess) {
         fdtd_set_error("fdtd_set_initial_conditions: upload failed");
         rc = FDTD_E_CUDA;

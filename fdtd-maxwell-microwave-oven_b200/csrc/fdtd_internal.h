@@ -23,6 +23,9 @@ void fdtd_set_error(const char *fmt, ...);
 double fdtd_factor_h(const fdtd_params *p);
 double fdtd_factor_e(const fdtd_params *p);
 
+/* set_initial_conditions(), main.c:416-424, for the node planes [k_first, k_first + nplanes) only */
+int fdtd_initial_conditions_planes(const fdtd_params *p, size_t k_first, size_t nplanes, double *Ey);
+
 #ifdef __cplusplus
 }
 #endif

@@ -150,28 +150,36 @@ int fdtd_source_values(const fdtd_params *p, const fdtd_source_plan *plan, doubl
     return FDTD_OK;
 }
 
-/* main.c:416-424.  The product sin(pi k dx / height) * sin(pi i dx / length) has only
- * (maxk+1) + (maxi+1) distinct factors; each is evaluated once with the same expression and the
- * same libm as the reference, so every product is bit-identical to the reference's. */
-int fdtd_initial_conditions_host(const fdtd_params *p, double *Ey)
+/* main.c:416-424, node planes [k_first, k_first + nplanes) only (a slab never needs more).
+ * The product sin(pi k dx / height) * sin(pi i dx / length) has only one factor per plane and one
+ * per column; each is evaluated once with the same expression and the same libm as the reference,
+ * so every product is bit-identical to the reference's. */
+int fdtd_initial_conditions_planes(const fdtd_params *p, size_t k_first, size_t nplanes, double *Ey)
 {
     size_t i, j, k;
     double *si;
     if (!p || !Ey) { fdtd_set_error("fdtd_initial_conditions_host: NULL argument"); return FDTD_E_ARG; }
+    if (k_first + nplanes > p->maxk + 1) { fdtd_set_error("fdtd_initial_conditions_host: planes out of range"); return FDTD_E_ARG; }
     si = (double *)malloc(sizeof(double) * (p->maxi + 1));
     if (!si) { fdtd_set_error("fdtd_initial_conditions_host: out of memory"); return FDTD_E_NOMEM; }
     for (i = 0; i < p->maxi + 1; ++i)
         si[i] = sin(FDTD_PI * i * p->spatial_step / p->length);
-    for (k = 0; k < p->maxk + 1; ++k) {
+    for (k = k_first; k < k_first + nplanes; ++k) {
         const double sk = sin(FDTD_PI * k * p->spatial_step / p->height);
         for (j = 0; j < p->maxj; ++j) {
-            double *row = Ey + (p->maxi + 1) * (j + p->maxj * k);
+            double *row = Ey + (p->maxi + 1) * (j + p->maxj * (k - k_first));
             for (i = 0; i < p->maxi + 1; ++i)
                 row[i] = sk * si[i];
         }
     }
     free(si);
     return FDTD_OK;
+}
+
+int fdtd_initial_conditions_host(const fdtd_params *p, double *Ey)
+{
+    if (!p) { fdtd_set_error("fdtd_initial_conditions_host: NULL argument"); return FDTD_E_ARG; }
+    return fdtd_initial_conditions_planes(p, 0, p->maxk + 1, Ey);
 }
 
 int fdtd_slab_range(size_t maxk, int rank, int nranks, size_t *k0, size_t *k1)
