@@ -1,11 +1,14 @@
 /*
- * fdtd_ctx.cu -- device context and C ABI of libfdtd_b200.so (declared in include/fdtd_b200.h).
+ * fdtd_ctx.cu -- device context, transfers, kernel launches, halo exchange and stepping: the core of
+ * libfdtd_b200.so's C ABI (include/fdtd_b200.h).  Dumps: fdtd_dump.cu; diagnostics: fdtd_diag.cu;
+ * all slabs from one thread: fdtd_group.cu; shared declarations: fdtd_ctx.hpp.
  *
  * One context = one z-slab of the cavity resident in the HBM of one B200: the six field arrays
- * in the pitched layout described in fdtd_kernels.cuh, a compute stream, a halo stream with its
+ * in the pitched layout described in fdtd_types.cuh, a compute stream, a halo stream with its
  * NCCL communicator, and a dump stream with pinned staging.  The host control thread only
  * queues work; nothing on the stepping path synchronises with the device.
- */#include "fdtd_ctx.hpp"
+ */
+#include "fdtd_ctx.hpp"
 #include "fdtd_update.cuh"
 #include "fdtd_fused.cuh"
 #include "fdtd_fused_tma.cuh"

@@ -11,15 +11,17 @@
  *        reference's dense rows (I or I+1 doubles, main.c:379-407) do not;
  *   R  = J + 1 rows per plane for every array;
  *   kl = local plane index.  A slab that owns the cell planes [k0, k1) stores global plane k at
- *        kl = k - k0 + 1.  Plane 0 receives the lower neighbour's Hx/Hy halo, plane nk + 1 the
- *        upper neighbour's Ex/Ey halo -- or, on the last slab, it IS the global node plane K.
+ *        kl = k - k0 + 1.  Plane 0 receives the lower neighbour's halo (Hx, Hy; for the fused step
+ *        also Ex, Ey, Ez), plane nk + 1 the upper neighbour's Ex/Ey halo -- or, on the last slab, it
+ *        IS the global node plane K.
  *   Padding (columns beyond an array's extent, the unused row/plane) is zero and never stored to.
  *
  * Arithmetic.  Every update is evaluated with explicit round-to-nearest intrinsics in the
  * reference's operand order (main.c:448-461, 486-499):
  *     F = F + c * ((a - b) - (d - e))
  * so no FMA can be formed whatever the compiler flags; the build also passes -fmad=false.
- */#pragma once
+ */
+#pragma once
 
 #include <cuda.h>
 #include <cuda_runtime.h>

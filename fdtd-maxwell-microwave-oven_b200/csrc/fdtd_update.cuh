@@ -2,7 +2,7 @@
  * fdtd_update.cuh -- the split update kernels: one launch per half-step, in place (144 B per
  * cell-update).  Variant 0 mirrors the reference's three operators one to one; variant 1 is the
  * z-marching register-strip form with source and PEC fused.  Layout and arithmetic: fdtd_types.cuh.
- * Included by fdtd_step.cu only.
+ * Included by fdtd_ctx.cu only.
  */
 #pragma once
 

@@ -6,7 +6,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from conftest import bits_equal, lower, to_oracle_params, upper
+from conftest import bits_equal, to_oracle_params, upper
 
 pytestmark = pytest.mark.gpu
 
