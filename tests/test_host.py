@@ -114,3 +114,46 @@ def test_pattern_and_checksum_mirrors_are_consistent(F):
     c["Hy"][1, 2, 3], c["Hy"][1, 2, 2] = c["Hy"][1, 2, 2], c["Hy"][1, 2, 3]  # a swap must show
     assert F.checksum_host(c)[4] != F.checksum_host(a)[4]
     assert F.checksum_host(c)[:4] == F.checksum_host(a)[:4]
+
+
+def test_host_program_cli_errors_without_gpu(F, tmp_path):
+    """The C host program's argument / file / parameter checks (main.c:811-821) come before any device
+    work, so they behave the same on a box without a GPU: perror text, exit status 1."""
+    import subprocess
+    exe = os.path.join(ROOT, "fdtd-maxwell-microwave-oven_b200", "microwave")
+    if not os.path.exists(exe):
+        import __graft_entry__
+        __graft_entry__.build()
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 1
+    assert r.stdout.splitlines() == ["Welcome into our microwave oven eletrico-magnetic field simulator! "]
+    assert r.stderr.startswith("This program needs 1 argument: the parameters file (.txt). Eg.: ./microwave param.txt")
+    r = subprocess.run([exe, "a", "b"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 1 and "This program needs 1 argument" in r.stderr
+    r = subprocess.run([exe, "missing.txt"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 1
+    assert r.stdout.splitlines()[-1] == "Loading the parameters..."
+    assert r.stderr.strip() == "Unable to open parameters file!: No such file or directory"
+    (tmp_path / "p.txt").write_text("0.012\n0.011\n0.010\n0.001\n0.0000000000006\n0.0000000000001\n3\n1")
+    r = subprocess.run([exe, "p.txt"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 1 and r.stderr.startswith("The time step must be lower than the simulation time!")
+
+
+def test_host_helpers_match_oracle_on_random_parameters(F, oracle, tmp_path):
+    """300 random parameter files: the grid derivation through float, the step count and the source
+    plan of the product agree with the oracle exactly (these decide everything downstream)."""
+    rng = np.random.default_rng(7)
+    o = oracle.restatement()
+    for _ in range(300):
+        dims = [f"{rng.uniform(0.003, 0.3):.{int(rng.integers(2, 7))}f}" for _ in range(3)]
+        dx = f"{rng.choice([0.001, 0.0005, 0.002, 0.00125]):g}"
+        dt = f"{rng.uniform(2e-13, 9e-13):.3e}"
+        sim = f"{rng.uniform(5e-12, 3e-10):.4e}"
+        nums = (*dims, dx, dt, sim, str(int(rng.integers(1, 60))), str(int(rng.integers(0, 2))))
+        path = oracle.write_params(tmp_path / "p.txt", nums)
+        a, b = F.load_parameters(path), o.load_parameters(path)
+        assert a.dims() == b.dims(), nums
+        assert F.step_count(a) == oracle.step_count(b), nums
+        plan = F.source_plan(a)
+        assert (plan.i0, plan.i1, plan.j0, plan.j1) == oracle.source_bounds(b), nums
+        assert plan.z_te == oracle.source_zte(b) or (np.isnan(plan.z_te) and np.isnan(oracle.source_zte(b))), nums
