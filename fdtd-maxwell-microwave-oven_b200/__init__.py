@@ -208,6 +208,12 @@ HALO_PLAN = {
     # as its plane k1 (read by its Hx/Hy update at cell plane k1-1, main.c:448-455)
     "after_E": {"fields": ("Ex", "Ey"), "send_plane": "k0", "to": -1, "recv_plane": "k1"},
 }
+# The fused step (kernels 2 and 3) exchanges once per time step: the slab above recomputes H_new of
+# the plane below its first one, so it needs that plane's Ex, Ey, Ez as well as Hx, Hy.
+HALO_PLAN_FUSED = {
+    "after_step_up": {"fields": ("Hx", "Hy", "Ex", "Ey", "Ez"), "send_plane": "k1-1", "to": +1, "recv_plane": "k0-1"},
+    "after_step_down": {"fields": ("Ex", "Ey"), "send_plane": "k0", "to": -1, "recv_plane": "k1"},
+}
 
 
 class PinnedArrays:
