@@ -359,7 +359,7 @@ int launch_fused_tma_t(fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cuda
     Span sp{kl_begin, kl_end, (int)std::max(c->opt_kchunk, 2L), 0};
     dim3 block(bx, wy);
     dim3 grid((c->g.I + 1 + bx - 1) / bx, (c->g.J + 1 + by - 1) / by, (kl_end - kl_begin + sp.kchunk - 1) / sp.kchunk);
-    k_step_fused_tma<TY, CWX, CWY><<<grid, block, smem, st>>>(c->g, c->tma_maps[0], c->f2, c->ch, c->ce, s, sp, stages);
+    k_step_fused_tma<TY, CWX, CWY><<<grid, block, smem, st>>>(c->g, c->tma_maps[0], c->f, c->f2, c->ch, c->ce, s, sp, stages);
     ++c->launches;
     return FDTD_OK;
 }

@@ -372,11 +372,38 @@ __device__ __forceinline__ void fused_tma_sweep(const Geo &g, const TmaMaps &map
     }
 }
 
+/* The node-centred arrays have I+1 columns.  For the usual power-of-two I the last block in x would
+ * hold the single column i = I and spend a whole chunk's time in the TMA pipeline for it, keeping an
+ * SM slot busy (11 % of the blocks at 1024^3 with 128-wide tiles, 33 % at 256^3).  That column only
+ * carries PEC values of Ey and Ez (copied) and the Hx update of main.c:448, so such a block does it
+ * directly, one (row, plane) per thread, and leaves. */
+__device__ __forceinline__ void last_column_sweep(const Geo &g, const Fld &a, const Fld &b, const double cH,
+                                                  const int by0, const int BY, const int kl0, const int kl1)
+{
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    const int items = BY * (kl1 - kl0);
+    for (int t = tid; t < items; t += nthr) {
+        const int j = by0 + t % BY, kl = kl0 + t / BY;
+        if (j > g.J)
+            continue;
+        const long long o = g.I + (long long)g.P * (j + (long long)g.R * kl);
+        const bool cell = kl <= g.nk;
+        if (j < g.J) {
+            const double ey = a.ey[o];
+            b.ey[o] = ey; /* Ey(I, j, k) is on the wall: carried over */
+            if (cell)
+                b.hx[o] = yee(a.hx[o], cH, a.ey[o + g.PR], ey, a.ez[o + g.P], a.ez[o]); /* main.c:448 */
+        }
+        if (cell)
+            b.ez[o] = a.ez[o]; /* Ez(I, j, k) is on the wall: carried over */
+    }
+}
+
 /* 256-thread blocks, two per SM -- or one 512-thread block for the largest tiles */
 template <int TY, int CWX, int CWY>
 __global__ void __launch_bounds__((CWX * CWY > 8) ? 512 : 256, (CWX * CWY > 8) ? 1 : 2)
-k_step_fused_tma(Geo g, const __grid_constant__ TmaMaps maps, Fld b, double cH, double cE, Src s, Span sp,
-                 int stages)
+k_step_fused_tma(Geo g, const __grid_constant__ TmaMaps maps, Fld a, Fld b, double cH, double cE, Src s,
+                 Span sp, int stages)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long full[kTmaMaxStages];
@@ -386,6 +413,11 @@ k_step_fused_tma(Geo g, const __grid_constant__ TmaMaps maps, Fld b, double cH, 
     const int by0 = blockIdx.y * blockDim.y * TY;
     const int kl0 = sp.kl_begin + blockIdx.z * sp.kchunk;
     const int kl1 = min(kl0 + sp.kchunk, sp.kl_end);
+
+    if (bx0 == g.I) { /* block-uniform: this block holds column I only */
+        last_column_sweep(g, a, b, cH, by0, (int)blockDim.y * TY, kl0, kl1);
+        return;
+    }
 
     if (threadIdx.x == 0 && threadIdx.y == 0) {
         for (int st = 0; st < stages; ++st)

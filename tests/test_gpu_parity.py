@@ -47,7 +47,9 @@ VARIANTS = [dict(kernel=0),
             dict(kernel=3, strip=2, kchunk=1000, warps_x=1, warps_y=8, stages=4),
             dict(kernel=3, strip=1, kchunk=2, warps_x=2, warps_y=4, stages=8)]
 GRIDS = [(0.037, 0.029, 0.023), (0.013, 0.011, 0.009), (0.05, 0.04, 0.03), (0.065, 0.033, 0.012),
-         (0.034, 0.066, 0.007)]
+         (0.034, 0.066, 0.007),
+         # I a multiple of the tile width: the last block in x holds the single column i = I
+         (0.0645, 0.0125, 0.0095), (0.1285, 0.0145, 0.0055)]
 
 
 def configure(ctx, variant):

@@ -16,6 +16,7 @@ ap.add_argument("--n", type=int, default=1024)
 ap.add_argument("--nz", type=int, default=512)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--quick", action="store_true")
+ap.add_argument("--small", action="store_true")
 ap.add_argument("--big", action="store_true")
 ap.add_argument("--fine", action="store_true")
 ap.add_argument("--tma", action="store_true")
@@ -56,6 +57,11 @@ if args.big:
     for kchunk, stages, (wx, wy) in itertools.product((32, 64), (2, 3), [(4, 4), (2, 8)]):
         variants.append(dict(kernel=3, strip=2, kchunk=kchunk, stages=stages, warps_x=wx, warps_y=wy))
     variants.append(dict(kernel=3, strip=2, kchunk=32, stages=3, warps_x=4, warps_y=2))
+if args.small:
+    variants = []
+    for kchunk, (wx, wy) in itertools.product((4, 8, 16, 32, 64), [(4, 2), (2, 2), (2, 4), (1, 8)]):
+        variants.append(dict(kernel=3, strip=2 if (wx, wy) != (1, 8) else 1, kchunk=kchunk, stages=3 if (wx, wy) != (1, 8) else 4, warps_x=wx, warps_y=wy))
+    variants.append(dict(kernel=1, strip=2, kchunk=8, warps_x=2, warps_y=2))
 if args.only is not None:
     variants = [v for v in variants if v["kernel"] == args.only or v["kernel"] == 0]
 
