@@ -345,8 +345,10 @@ TRAFFIC_BYTES_PER_CELL_HALF_STEP = 20.022561e9 / (1024 * 1024 * 256)
 TRAFFIC_SOURCE = "profiles/r01_split_ncu_full_raw.csv (k_update_h_march<2>, 20.02 GB per launch at 1024x1024x256)"
 # same for the fused TMA step (None until captured)
 TRAFFIC_FUSED_BYTES_PER_CELL = (14.695572e9 + 12.960834e9) / (1024 * 1024 * 256)
-TRAFFIC_FUSED_SOURCE = ("profiles/r01_tma_ncu_full_raw.csv (k_step_fused_tma<2,4,2>, 14.70 GB read + 12.96 GB written "
-                        "per launch at 1024x1024x256; the fused sweep's minimum is 96 B x cells = 25.77 GB)")
+TRAFFIC_FUSED_SOURCE = ("profiles/r01_tma_ncu_full_raw.csv (k_step_fused_tma<2,4,2>, i.e. the 128x4 tile: 14.70 GB read + "
+                        "12.96 GB written per launch at 1024x1024x256; the fused sweep's minimum is 96 B x cells = "
+                        "25.77 GB).  The default tile became 32x8 (k_step_fused_tma<1,1,8>) at the very end of round 1, "
+                        "after this capture; its traffic has not been re-captured")
 
 if __name__ == "__main__":
     main()

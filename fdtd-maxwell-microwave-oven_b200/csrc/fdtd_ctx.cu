@@ -823,15 +823,16 @@ int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx
     }
     c->ch = fdtd_factor_h(p);
     c->ce = fdtd_factor_e(p);
-    /* default: the TMA-staged fused step with the launch shape that won the sweep on a B200
-     * (profiles/): 128 x 4 tile, 2 rows per thread, 32 planes per block, 3 stages in flight */
+    /* default: the TMA-staged fused step with the launch shape that won the sweeps on a B200 at
+     * 256^3, 512^3 and 1024^3 (profiles/): 32 x 8 tile, one row per thread, 32 planes per block,
+     * 4 stages in flight */
     c->opt_kernel = 3;
     c->kernel_auto = true;
-    c->opt_strip = 2;
+    c->opt_strip = 1;
     c->opt_kchunk = 32;
-    c->opt_wx = 4;
-    c->opt_wy = 2;
-    c->opt_stages = 3;
+    c->opt_wx = 1;
+    c->opt_wy = 8;
+    c->opt_stages = 4;
     c->opt_prefetch = 3;
 
     rc = fdtd_source_plan_make(p, &c->plan);
