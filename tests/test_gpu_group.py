@@ -119,3 +119,25 @@ def test_microwave_with_two_gpus(F, golden, tmp_path):
             whole = np.concatenate([parts[rr][v * nx * ny * (k[rr][1] - k[rr][0]):(v + 1) * nx * ny * (k[rr][1] - k[rr][0])]
                                     for rr in range(2)])
             assert digest(whole) == d["vars"][name], (base, name)
+
+
+@pytest.mark.parametrize("dims,mode", [((64, 21, 11), 1), ((32, 40, 9), 0), ((96, 17, 8), 1)])
+def test_group_default_kernel_when_the_last_block_holds_one_column(F, oracle, dims, mode):
+    """I a multiple of the tile width: the default kernel's last block in x holds the single column
+    i = I and takes the direct path (last_column_sweep); slabs must still match the oracle.
+    (tools/check_last_column_slabs.py is the same check as a script.)"""
+    if ngpu() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    o = oracle.restatement()
+    for world in sorted({2, min(ngpu(), 4)}):
+        args = tuple((d + .5) * 1e-3 for d in dims) + (0.001, 6e-13, 1.2e-10, 2, mode)
+        p, q = F.make_params(*args), oracle.make_params(*args)
+        assert p.dims() == dims
+        f = oracle.alloc_fields(*dims, rng=np.random.default_rng(3))
+        with F.Group(p, world) as g:
+            g.upload(upper(f))
+            g.run(5, 0.0)
+            o.run(q, f, 5)
+            got = g.download()
+        for k, want in f.items():
+            assert bits_equal(got[k[0].upper() + k[1:]], want), (world, k)
