@@ -14,6 +14,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FDTD_B200_LIB") or os.path.join(HERE, "libfdtd_b200.so")  # override: A/B of two builds
+PEER_BLOB_BYTES = 384  # FDTD_PEER_BLOB_BYTES
 FIELD_NAMES = ("Ex", "Ey", "Ez", "Hx", "Hy", "Hz")
 DUMP_NAMES = ("ex", "ey", "ez", "hx", "hy", "hz")
 
@@ -82,6 +83,8 @@ SIGNATURES = {
     "fdtd_ctx_destroy": (C.c_int, [_CTX]),
     "fdtd_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "fdtd_ctx_comm_init": (C.c_int, [_CTX, C.c_void_p]),
+    "fdtd_ctx_peer_export": (C.c_int, [_CTX, C.c_void_p]),
+    "fdtd_ctx_peer_connect": (C.c_int, [_CTX, C.c_void_p]),
     "fdtd_ctx_set_option": (C.c_int, [_CTX, C.c_char_p, C.c_long]),
     "fdtd_ctx_get_option": (C.c_int, [_CTX, C.c_char_p, C.POINTER(C.c_long)]),
     "fdtd_upload": (C.c_int, [_CTX, C.POINTER(FieldPtrs)]),
@@ -96,9 +99,11 @@ SIGNATURES = {
     "fdtd_run_timed": (C.c_int, [_CTX, C.c_size_t, _D, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                  C.POINTER(C.c_float)]),
     "fdtd_sync": (C.c_int, [_CTX]),
+    "fdtd_run_hosted": (C.c_int, [_CTX, C.POINTER(FieldPtrs), C.c_size_t, _D]),
     "fdtd_aggregate": (C.c_int, [_CTX, C.c_int, _D]),
     "fdtd_propagate": (C.c_int, [_CTX, C.POINTER(DumpSink), C.POINTER(C.c_size_t), _D]),
     "fdtd_group_create": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
+    "fdtd_group_create_transport": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
     "fdtd_group_destroy": (C.c_int, [C.c_void_p]),
     "fdtd_group_size": (C.c_int, [C.c_void_p]),
     "fdtd_group_ctx": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_CTX)]),
@@ -283,6 +288,18 @@ class Context:
     def comm_init(self, unique_id: bytes):
         _check(lib.fdtd_ctx_comm_init(self._h, C.create_string_buffer(unique_id, 128)))
 
+    def peer_export(self) -> bytes:
+        """descriptor of this slab's state for fdtd_ctx_peer_connect on the other ranks"""
+        buf = C.create_string_buffer(PEER_BLOB_BYTES)
+        _check(lib.fdtd_ctx_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_connect(self, blobs):
+        """blobs: the peer_export() of every rank, in rank order"""
+        table = b"".join(blobs)
+        assert len(table) == PEER_BLOB_BYTES * self.nranks
+        _check(lib.fdtd_ctx_peer_connect(self._h, C.create_string_buffer(table, len(table))))
+
     def set_option(self, key, value):
         _check(lib.fdtd_ctx_set_option(self._h, key.encode(), int(value)))
 
@@ -350,6 +367,12 @@ class Context:
     def sync(self):
         _check(lib.fdtd_sync(self._h))
 
+    def run_hosted(self, fields, steps, t=0.0):
+        """advance host arrays (this slab's planes, dense layout) in place by `steps` time steps"""
+        tc = C.c_double(t)
+        _check(lib.fdtd_run_hosted(self._h, C.byref(_ptrs(fields)), int(steps), C.byref(tc)))
+        return tc.value
+
     def aggregate(self, var):
         nx, ny, _ = self.p.dims()
         out = np.empty((self.k1 - self.k0, ny, nx))
@@ -404,11 +427,17 @@ class Context:
 class Group:
     """fdtd_group: every z-slab of the cavity driven from this one thread (no launcher)."""
 
-    def __init__(self, p: Params, ngpus, devices=None):
+    def __init__(self, p: Params, ngpus, devices=None, transport=None):
+        """transport: None (FDTD_B200_TRANSPORT or peer copies), "peer" or "nccl"; devices may repeat
+        (several slabs on one GPU) with peer copies"""
         self.p = p
         self._g = C.c_void_p()
         dev = (C.c_int * ngpus)(*devices) if devices is not None else None
-        _check(lib.fdtd_group_create(C.byref(p), ngpus, dev, C.byref(self._g)))
+        if transport is None:
+            _check(lib.fdtd_group_create(C.byref(p), ngpus, dev, C.byref(self._g)))
+        else:
+            _check(lib.fdtd_group_create_transport(C.byref(p), ngpus, dev, {"peer": 0, "nccl": 1}[transport],
+                                                   C.byref(self._g)))
         self.n = lib.fdtd_group_size(self._g)
         self.slabs = []
         for r in range(self.n):

@@ -17,43 +17,6 @@ using namespace fdtdi;
 
 namespace fdtdi {
 
-NcclApi g_nccl;
-
-int nccl_bind()
-{
-    static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
-    pthread_mutex_lock(&mu);
-    if (!g_nccl.ok) {
-        const char *name = getenv("FDTD_B200_NCCL_LIB");
-        void *h = name ? dlopen(name, RTLD_NOW | RTLD_GLOBAL) : dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
-        if (!h && !name)
-            h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-        if (h) {
-#define BIND(field, sym) *(void **)(&g_nccl.field) = dlsym(h, sym)
-            BIND(GetUniqueId, "ncclGetUniqueId");
-            BIND(CommInitRank, "ncclCommInitRank");
-            BIND(CommInitAll, "ncclCommInitAll");
-            BIND(CommDestroy, "ncclCommDestroy");
-            BIND(Send, "ncclSend");
-            BIND(Recv, "ncclRecv");
-            BIND(GroupStart, "ncclGroupStart");
-            BIND(GroupEnd, "ncclGroupEnd");
-            BIND(GetErrorString, "ncclGetErrorString");
-#undef BIND
-            g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommInitAll && g_nccl.CommDestroy && g_nccl.Send &&
-                        g_nccl.Recv && g_nccl.GroupStart && g_nccl.GroupEnd && g_nccl.GetErrorString;
-        }
-    }
-    const bool ok = g_nccl.ok;
-    pthread_mutex_unlock(&mu);
-    if (!ok) {
-        fdtd_set_error("cannot load NCCL (libnccl.so.2): %s", dlerror() ? dlerror() : "symbols missing");
-        return FDTD_E_NCCL;
-    }
-    return FDTD_OK;
-}
-
-
 int check_ctx(const fdtd_ctx *c, const char *who)
 {
     if (!c) {
@@ -61,7 +24,8 @@ int check_ctx(const fdtd_ctx *c, const char *who)
         return FDTD_E_ARG;
     }
     if (c->opt_wx * c->opt_wy > (c->opt_kernel == 3 ? 16 : 8)) { /* a block is at most 256 threads (512 for the TMA kernel) */
-        fdtd_set_error("%s: options warps_x (%ld) * warps_y (%ld) must be <= 8", who, c->opt_wx, c->opt_wy);
+        fdtd_set_error("%s: options warps_x (%ld) * warps_y (%ld) must be <= %d for kernel %ld", who, c->opt_wx, c->opt_wy,
+                       c->opt_kernel == 3 ? 16 : 8, c->opt_kernel);
         return FDTD_E_ARG;
     }
     return FDTD_OK;
@@ -102,17 +66,18 @@ DenseShape dense_shape(const fdtd_params &p, int idx)
     }
 }
 
-/* copy the planes this slab owns between the dense host array and the pitched device array */
-int copy_field(fdtd_ctx *c, int idx, double *host_first_owned_plane, bool to_device)
+/* copy local planes [kl0, kl1) (clipped to the planes this slab owns of array idx) between the dense
+ * host array -- host_first_owned_plane addresses local plane 1 -- and the pitched device array */
+int copy_planes(fdtd_ctx *c, int idx, double *host_first_owned_plane, int kl0, int kl1, bool to_device, cudaStream_t st)
 {
     const DenseShape s = dense_shape(c->p, idx);
-    size_t nplanes = c->g.nk;
-    if (s.node_planes && c->g.top)
-        nplanes += 1;
-    if (nplanes == 0 || s.w == 0 || s.h == 0)
+    const int last = c->g.nk + ((s.node_planes && c->g.top) ? 1 : 0); /* last owned local plane */
+    kl0 = std::max(kl0, 1);
+    kl1 = std::min(kl1, last + 1);
+    if (kl1 <= kl0 || s.w == 0 || s.h == 0)
         return FDTD_OK;
-    double *dev = field_ptr(c, idx) + (size_t)c->g.PR; /* local plane 1 */
-    double *hst = host_first_owned_plane;
+    double *dev = field_ptr(c, idx) + (size_t)c->g.PR * (size_t)kl0;
+    double *hst = host_first_owned_plane + (size_t)(kl0 - 1) * s.w * s.h;
     cudaMemcpy3DParms m;
     memset(&m, 0, sizeof m);
     cudaPitchedPtr hp = make_cudaPitchedPtr(hst, s.w * sizeof(double), s.w * sizeof(double), s.h);
@@ -120,10 +85,16 @@ int copy_field(fdtd_ctx *c, int idx, double *host_first_owned_plane, bool to_dev
                                             (size_t)c->g.P * sizeof(double), (size_t)c->g.R);
     m.srcPtr = to_device ? hp : dp;
     m.dstPtr = to_device ? dp : hp;
-    m.extent = make_cudaExtent(s.w * sizeof(double), s.h, nplanes);
+    m.extent = make_cudaExtent(s.w * sizeof(double), s.h, (size_t)(kl1 - kl0));
     m.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
-    CUDA_TRY(cudaMemcpy3DAsync(&m, c->s_main));
+    CUDA_TRY(cudaMemcpy3DAsync(&m, st));
     return FDTD_OK;
+}
+
+/* all the planes this slab owns */
+int copy_field(fdtd_ctx *c, int idx, double *host_first_owned_plane, bool to_device)
+{
+    return copy_planes(c, idx, host_first_owned_plane, 1, c->g.nk + 2, to_device, c->s_main);
 }
 
 Src make_src(const fdtd_ctx *c, const double *row)
@@ -227,7 +198,10 @@ void launch_e(const fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStr
  * first array and up to two planes and a few rows past the last one.  Those values are never
  * used for a stored result; the margins only keep the addresses inside the allocation. */
 size_t margin_front(const fdtd_ctx *c) { return (size_t)c->g.P + 64; }
-size_t margin_back(const fdtd_ctx *c) { return 2 * (size_t)c->g.PR + 8 * (size_t)c->g.P + 1024; }
+/* back: the unpredicated kernel (k_step_fused) reads, from an edge block of the last plane, up to
+ * one plane plus a block's rows (at most 8 warps x 4 rows) plus a block's columns (256) further */
+size_t margin_back(const fdtd_ctx *c) { return 2 * (size_t)c->g.PR + 40 * (size_t)c->g.P + 2048; }
+size_t margin_front_of(const fdtd_ctx *c) { return margin_front(c); }
 
 /* one zero-filled set of six arrays (padding must be zero and stays zero) */
 cudaError_t alloc_state(fdtd_ctx *c, double **raw, double **base)
@@ -262,6 +236,7 @@ int ensure_pong(fdtd_ctx *c)
 
 void swap_buffers(fdtd_ctx *c)
 {
+    c->flip ^= 1;
     std::swap(c->raw, c->raw2);
     std::swap(c->base, c->base2);
     std::swap(c->f, c->f2);
@@ -411,103 +386,12 @@ void launch_set_source(const fdtd_ctx *c, const double *row_dev, cudaStream_t st
     ++c->launches;
 }
 
-/* ---- halo exchange (one plane each way per half-step) ----------------------- */
-
-/* Hx, Hy of my top cell plane go up; the lower neighbour's arrive in my plane 0.
- * with_e: also Ex, Ey, Ez of that plane -- the fused step recomputes H of the plane below its
- * slab and needs the E around it (fdtd_fused.cuh). */
-int exchange_h(fdtd_ctx *c, cudaStream_t st, bool with_e)
-{
-    if (c->nranks == 1)
-        return FDTD_OK;
-    if (!c->has_comm) {
-        fdtd_set_error("multi-rank context without communicator: call fdtd_ctx_comm_init first");
-        return FDTD_E_STATE;
-    }
-    const size_t n = (size_t)c->g.PR;
-    double *up[5] = {c->f.hx, c->f.hy, c->f.ex, c->f.ey, c->f.ez};
-    const int count = with_e ? 5 : 2;
-    NCCL_TRY(g_nccl.GroupStart());
-    if (c->rank + 1 < c->nranks)
-        for (int a = 0; a < count; ++a)
-            NCCL_TRY(g_nccl.Send(up[a] + n * c->g.nk, n, ncclDouble, c->rank + 1, c->comm, st));
-    if (c->rank > 0)
-        for (int a = 0; a < count; ++a)
-            NCCL_TRY(g_nccl.Recv(up[a], n, ncclDouble, c->rank - 1, c->comm, st));
-    NCCL_TRY(g_nccl.GroupEnd());
-    return FDTD_OK;
-}
-
-/* Ex, Ey of my first node plane go down; the upper neighbour's arrive in my plane nk+1.
- * with_hz: also Hz (only the dump's zone average needs it, main.c:578). */
-int exchange_e(fdtd_ctx *c, cudaStream_t st, bool with_hz)
-{
-    if (c->nranks == 1)
-        return FDTD_OK;
-    if (!c->has_comm) {
-        fdtd_set_error("multi-rank context without communicator: call fdtd_ctx_comm_init first");
-        return FDTD_E_STATE;
-    }
-    const size_t n = (size_t)c->g.PR;
-    NCCL_TRY(g_nccl.GroupStart());
-    if (c->rank > 0) {
-        NCCL_TRY(g_nccl.Send(c->f.ex + n, n, ncclDouble, c->rank - 1, c->comm, st));
-        NCCL_TRY(g_nccl.Send(c->f.ey + n, n, ncclDouble, c->rank - 1, c->comm, st));
-        if (with_hz)
-            NCCL_TRY(g_nccl.Send(c->f.hz + n, n, ncclDouble, c->rank - 1, c->comm, st));
-    }
-    if (c->rank + 1 < c->nranks) {
-        NCCL_TRY(g_nccl.Recv(c->f.ex + n * (c->g.nk + 1), n, ncclDouble, c->rank + 1, c->comm, st));
-        NCCL_TRY(g_nccl.Recv(c->f.ey + n * (c->g.nk + 1), n, ncclDouble, c->rank + 1, c->comm, st));
-        if (with_hz)
-            NCCL_TRY(g_nccl.Recv(c->f.hz + n * (c->g.nk + 1), n, ncclDouble, c->rank + 1, c->comm, st));
-    }
-    NCCL_TRY(g_nccl.GroupEnd());
-    return FDTD_OK;
-}
-
-/* Work on the compute stream that touches halo planes (dump exchange, diagnostics) must come after
- * whatever the halo stream still has in flight from the last step. */
-int join_halo_stream(fdtd_ctx *c)
-{
-    if (c->nranks > 1) {
-        CUDA_TRY(cudaStreamWaitEvent(c->s_main, c->ev_ehalo, 0));
-        CUDA_TRY(cudaStreamWaitEvent(c->s_main, c->ev_hhalo, 0));
-    }
-    return FDTD_OK;
-}
-
-/* make the halos the selected kernel needs current, on the compute stream (after upload /
- * operator-level calls).  The flags are set identically on every rank, so the sends and
- * receives always pair up. */
-int refresh_halos(fdtd_ctx *c)
-{
-    if (c->nranks == 1)
-        return FDTD_OK;
-    const bool fused = c->opt_kernel >= 2;
-    if (!c->e_halo_valid || !c->h_halo_valid || (fused && !c->low_e_halo_valid))
-        FDTD_TRY(join_halo_stream(c));
-    if (!c->e_halo_valid) {
-        FDTD_TRY(exchange_e(c, c->s_main, false));
-        c->e_halo_valid = true;
-    }
-    if (!c->h_halo_valid || (fused && !c->low_e_halo_valid)) {
-        FDTD_TRY(exchange_h(c, c->s_main, fused));
-        c->h_halo_valid = true;
-        c->low_e_halo_valid = fused;
-    }
-    return FDTD_OK;
-}
-
 /* A time step is made of segments -- one for the fused kernels (H and E in one sweep), two for the
- * split kernels (H half-step, E half-step).  Each segment has three parts so that several slabs
- * driven by ONE host thread (fdtd_group_*) can put all their NCCL calls of a segment into a single
- * NCCL group:
- *   seg_launch    everything on the compute stream: wait for the halos of the previous segment,
- *                 boundary plane(s) first, event, interior planes; the halo stream is told to wait
- *                 for the boundary event (the halo traffic hides behind the interior planes);
- *   seg_exchange  the ncclSend / ncclRecv calls on the halo stream;
- *   seg_finish    the "halo has arrived" events the next segment waits for. */
+ * split kernels (H half-step, E half-step).  seg_launch queues a segment's kernels on the compute
+ * stream: wait for the halos of the previous segment, boundary plane(s) first, the ev_bnd event,
+ * then the interior planes; exchange_many(seg_xchg(seg), on_comm = true) then moves the boundary
+ * planes on the halo streams while the interior planes run (fdtd_halo.cu).  The two are separate so
+ * that one host thread can drive every slab of a group: all launches, then all transfers. */
 int seg_launch(fdtd_ctx *c, const Src &s, Segment seg)
 {
     FDTD_TRY(use_device(c));
@@ -515,17 +399,17 @@ int seg_launch(fdtd_ctx *c, const Src &s, Segment seg)
     const int h_end = nk + c->g.top + 1; /* exclusive */
     const bool multi = c->nranks > 1;
     const bool sends_up = c->rank + 1 < c->nranks, sends_down = c->rank > 0;
+    if (multi)
+        FDTD_TRY(wait_halos(c));
     if (seg == SEG_FUSED) {
         /* reads c->f, writes c->f2, then the two swap */
         if (!multi) {
             launch_fused(c, s, 1, h_end, c->s_main);
             swap_buffers(c);
         } else {
-            CUDA_TRY(cudaStreamWaitEvent(c->s_main, c->ev_ehalo, 0));
-            CUDA_TRY(cudaStreamWaitEvent(c->s_main, c->ev_hhalo, 0));
             if (nk < 3) {
                 launch_fused(c, s, 1, h_end, c->s_main);
-                CUDA_TRY(cudaEventRecord(c->ev_hb, c->s_main));
+                CUDA_TRY(cudaEventRecord(c->ev_bnd, c->s_main));
             } else {
                 int lo = 1, hi = h_end;
                 if (sends_up) { /* top owned plane first: 5 arrays of it travel up */
@@ -536,11 +420,10 @@ int seg_launch(fdtd_ctx *c, const Src &s, Segment seg)
                     launch_fused(c, s, 1, 2, c->s_main);
                     lo = 2;
                 }
-                CUDA_TRY(cudaEventRecord(c->ev_hb, c->s_main));
+                CUDA_TRY(cudaEventRecord(c->ev_bnd, c->s_main));
                 launch_fused(c, s, lo, hi, c->s_main);
             }
             swap_buffers(c); /* the exchange works on the new state */
-            CUDA_TRY(cudaStreamWaitEvent(c->s_comm, c->ev_hb, 0));
         }
         if (c->launch_error != FDTD_OK) {
             const int rc = c->launch_error;
@@ -552,34 +435,26 @@ int seg_launch(fdtd_ctx *c, const Src &s, Segment seg)
             launch_set_source(c, s.vals, c->s_main);
         if (!multi) {
             launch_h(c, s, 1, h_end, c->s_main);
+        } else if (sends_up) {
+            launch_h(c, s, nk, nk + 1, c->s_main); /* boundary plane first */
+            CUDA_TRY(cudaEventRecord(c->ev_bnd, c->s_main));
+            launch_h(c, s, 1, nk, c->s_main);
         } else {
-            CUDA_TRY(cudaStreamWaitEvent(c->s_main, c->ev_ehalo, 0)); /* Ex, Ey of plane nk+1 arrived */
-            if (sends_up) {
-                launch_h(c, s, nk, nk + 1, c->s_main); /* boundary plane first */
-                CUDA_TRY(cudaEventRecord(c->ev_hb, c->s_main));
-                launch_h(c, s, 1, nk, c->s_main);
-            } else {
-                launch_h(c, s, 1, h_end, c->s_main);
-                CUDA_TRY(cudaEventRecord(c->ev_hb, c->s_main));
-            }
-            CUDA_TRY(cudaStreamWaitEvent(c->s_comm, c->ev_hb, 0));
+            launch_h(c, s, 1, h_end, c->s_main);
+            CUDA_TRY(cudaEventRecord(c->ev_bnd, c->s_main));
         }
     } else {
         if (c->opt_kernel == 0 && c->src_here)
             launch_set_source(c, s.vals, c->s_main);
         if (!multi) {
             launch_e(c, s, 1, nk + 1, c->s_main);
+        } else if (sends_down) {
+            launch_e(c, s, 1, 2, c->s_main);
+            CUDA_TRY(cudaEventRecord(c->ev_bnd, c->s_main));
+            launch_e(c, s, 2, nk + 1, c->s_main);
         } else {
-            CUDA_TRY(cudaStreamWaitEvent(c->s_main, c->ev_hhalo, 0)); /* Hx, Hy of plane 0 arrived */
-            if (sends_down) {
-                launch_e(c, s, 1, 2, c->s_main);
-                CUDA_TRY(cudaEventRecord(c->ev_eb, c->s_main));
-                launch_e(c, s, 2, nk + 1, c->s_main);
-            } else {
-                launch_e(c, s, 1, nk + 1, c->s_main);
-                CUDA_TRY(cudaEventRecord(c->ev_eb, c->s_main));
-            }
-            CUDA_TRY(cudaStreamWaitEvent(c->s_comm, c->ev_eb, 0));
+            launch_e(c, s, 1, nk + 1, c->s_main);
+            CUDA_TRY(cudaEventRecord(c->ev_bnd, c->s_main));
         }
         c->low_e_halo_valid = false; /* the split kernels refresh only Hx, Hy of plane 0 */
     }
@@ -587,32 +462,14 @@ int seg_launch(fdtd_ctx *c, const Src &s, Segment seg)
     return FDTD_OK;
 }
 
-int seg_exchange(fdtd_ctx *c, Segment seg)
+Xchg seg_xchg(Segment seg)
 {
-    if (c->nranks == 1)
-        return FDTD_OK;
-    FDTD_TRY(use_device(c));
-    if (seg == SEG_FUSED) {
-        FDTD_TRY(exchange_h(c, c->s_comm, true));
-        FDTD_TRY(exchange_e(c, c->s_comm, false));
-    } else if (seg == SEG_H) {
-        FDTD_TRY(exchange_h(c, c->s_comm, false));
-    } else {
-        FDTD_TRY(exchange_e(c, c->s_comm, false));
-    }
-    return FDTD_OK;
-}
-
-int seg_finish(fdtd_ctx *c, Segment seg)
-{
-    if (c->nranks == 1)
-        return FDTD_OK;
-    FDTD_TRY(use_device(c));
-    if (seg == SEG_FUSED || seg == SEG_H)
-        CUDA_TRY(cudaEventRecord(c->ev_hhalo, c->s_comm));
-    if (seg == SEG_FUSED || seg == SEG_E)
-        CUDA_TRY(cudaEventRecord(c->ev_ehalo, c->s_comm));
-    return FDTD_OK;
+    Xchg x;
+    x.h = seg == SEG_FUSED || seg == SEG_H;
+    x.h_with_e = seg == SEG_FUSED;
+    x.e = seg == SEG_FUSED || seg == SEG_E;
+    x.e_with_hz = false;
+    return x;
 }
 
 /* One pass of the loop body main.c:770-779 for one context (one process per GPU). */
@@ -622,19 +479,16 @@ int queue_step(fdtd_ctx *c, const Src &s, cudaEvent_t ev_h_begin, cudaEvent_t ev
         CUDA_TRY(cudaEventRecord(ev_h_begin, c->s_main));
     if (c->opt_kernel >= 2) {
         FDTD_TRY(seg_launch(c, s, SEG_FUSED));
-        FDTD_TRY(seg_exchange(c, SEG_FUSED));
-        FDTD_TRY(seg_finish(c, SEG_FUSED));
+        FDTD_TRY(exchange_many(&c, 1, seg_xchg(SEG_FUSED), true));
         if (ev_mid)
             CUDA_TRY(cudaEventRecord(ev_mid, c->s_main));
     } else {
         FDTD_TRY(seg_launch(c, s, SEG_H));
-        FDTD_TRY(seg_exchange(c, SEG_H));
-        FDTD_TRY(seg_finish(c, SEG_H));
+        FDTD_TRY(exchange_many(&c, 1, seg_xchg(SEG_H), true));
         if (ev_mid)
             CUDA_TRY(cudaEventRecord(ev_mid, c->s_main));
         FDTD_TRY(seg_launch(c, s, SEG_E));
-        FDTD_TRY(seg_exchange(c, SEG_E));
-        FDTD_TRY(seg_finish(c, SEG_E));
+        FDTD_TRY(exchange_many(&c, 1, seg_xchg(SEG_E), true));
     }
     if (ev_e_end)
         CUDA_TRY(cudaEventRecord(ev_e_end, c->s_main));
@@ -664,34 +518,63 @@ int stage_source_rows(fdtd_ctx *c, size_t count, double *t_io)
 
 /* The fused step needs the state twice in HBM; when that does not fit and the caller did not ask
  * for a particular kernel, the in-place split kernels (144 B per cell-update instead of 96) take
- * over -- still on the GPU. */
+ * over -- still on the GPU, and never silently: a line on stderr, and the options "fallback" and
+ * "kernel" report it. */
 void fall_back_to_split(fdtd_ctx *c)
 {
     cudaGetLastError();
+    if (!c->fallback && c->rank == 0)
+        fprintf(stderr, "[fdtd_b200] the fused step needs a second copy of the state (%.1f GB per slab) which does not "
+                        "fit in HBM on every slab: using the in-place split kernels (kernel=1) instead\n",
+                6e-9 * (double)c->array_elems * sizeof(double));
+    c->fallback = 1;
     c->opt_kernel = 1;
     c->opt_strip = 2;
     c->opt_kchunk = 8;
     c->opt_wx = 2;
     c->opt_wy = 2;
+    if (c->raw2 && !c->n_ipc) {
+        cudaFree(c->raw2);
+        c->raw2 = c->base2 = nullptr;
+    }
+}
+
+/* Decide, identically on every slab, whether the fused kernels can run.  A single context decides
+ * alone; slabs of one process per GPU agreed when they were wired (fdtd_ctx_comm_init /
+ * fdtd_ctx_peer_connect); a group decides in group_run. */
+int settle_kernel(fdtd_ctx *c)
+{
+    if (c->opt_kernel < 2)
+        return FDTD_OK;
+    if (c->nranks == 1) {
+        const int rc = ensure_pong(c);
+        if (rc == FDTD_E_NOMEM && c->kernel_auto) {
+            fall_back_to_split(c);
+            return FDTD_OK;
+        }
+        return rc;
+    }
+    if (!c->wired) {
+        fdtd_set_error("multi-rank context is not wired to its neighbours: call fdtd_ctx_comm_init or "
+                       "fdtd_ctx_peer_connect first");
+        return FDTD_E_STATE;
+    }
+    if (c->fused_ok)
+        return ensure_pong(c); /* already there */
+    if (c->kernel_auto) {
+        fall_back_to_split(c);
+        return FDTD_OK;
+    }
+    fdtd_set_error("the fused kernels (kernel >= 2) need a second copy of the state on every slab; it was not "
+                   "available when the slabs were wired (select the kernel before wiring, or use kernel 0/1)");
+    return FDTD_E_NOMEM;
 }
 
 int run_impl(fdtd_ctx *c, size_t steps, double *time_counter, float *total_ms, float *h_ms, float *e_ms)
 {
     FDTD_TRY(use_device(c));
-    if (c->opt_kernel >= 2) {
-        int rc = ensure_pong(c);
-        if (rc == FDTD_E_NOMEM && c->kernel_auto) {
-            fall_back_to_split(c);
-        } else if (rc != FDTD_OK) {
-            return rc;
-        }
-    }
-    FDTD_TRY(refresh_halos(c));
-    if (c->nranks > 1) {
-        /* the first step's waits need recorded events */
-        CUDA_TRY(cudaEventRecord(c->ev_ehalo, c->s_main));
-        CUDA_TRY(cudaEventRecord(c->ev_hhalo, c->s_main));
-    }
+    FDTD_TRY(settle_kernel(c));
+    FDTD_TRY(refresh_halos_many(&c, 1, c->opt_kernel >= 2));
     const bool timed = total_ms != nullptr;
     const bool per_kernel = timed && (h_ms || e_ms);
     const size_t max_kernel_events = 2048;
@@ -834,6 +717,8 @@ int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx
     c->opt_wy = 8;
     c->opt_stages = 4;
     c->opt_prefetch = 3;
+    c->opt_host_chunk = 0; /* automatic */
+    c->opt_host_pipeline = 1;
 
     rc = fdtd_source_plan_make(p, &c->plan);
     if (rc != FDTD_OK) {
@@ -879,8 +764,8 @@ int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx
     CREATE_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CREATE_TRY(cudaStreamCreateWithPriority(&c->s_comm, cudaStreamNonBlocking, hi));
     CREATE_TRY(cudaStreamCreateWithPriority(&c->s_dump, cudaStreamNonBlocking, lo));
-    CREATE_TRY(cudaEventCreateWithFlags(&c->ev_hb, cudaEventDisableTiming));
-    CREATE_TRY(cudaEventCreateWithFlags(&c->ev_eb, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&c->ev_bnd, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&c->ev_sent, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&c->ev_hhalo, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&c->ev_ehalo, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&c->ev_src, cudaEventDisableTiming));
@@ -922,58 +807,26 @@ int fdtd_ctx_destroy(fdtd_ctx *c)
     if (!c)
         return FDTD_OK;
     cudaSetDevice(c->device);
+    if (c->s_main && c->wired) wait_halos(c);
     if (c->s_main) cudaStreamSynchronize(c->s_main);
     if (c->s_comm) cudaStreamSynchronize(c->s_comm);
     if (c->s_dump) cudaStreamSynchronize(c->s_dump);
     pipe_destroy(c);
-    if (c->has_comm) g_nccl.CommDestroy(c->comm);
+    halo_destroy(c);
     if (c->raw) cudaFree(c->raw);
     if (c->raw2) cudaFree(c->raw2);
     if (c->src_dev) cudaFree(c->src_dev);
     if (c->src_one_dev) cudaFree(c->src_one_dev);
     if (c->src_host) cudaFreeHost(c->src_host);
     if (c->agg_dev) cudaFree(c->agg_dev);
-    cudaEvent_t evs[] = {c->ev_hb, c->ev_eb, c->ev_hhalo, c->ev_ehalo, c->ev_src};
+    cudaEvent_t evs[] = {c->ev_bnd, c->ev_sent, c->ev_hhalo, c->ev_ehalo, c->ev_src};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
     if (c->s_main) cudaStreamDestroy(c->s_main);
     if (c->s_comm) cudaStreamDestroy(c->s_comm);
     if (c->s_dump) cudaStreamDestroy(c->s_dump);
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     delete c;
-    return FDTD_OK;
-}
-
-int fdtd_nccl_unique_id(void *id128)
-{
-    if (!id128) {
-        fdtd_set_error("fdtd_nccl_unique_id: NULL argument");
-        return FDTD_E_ARG;
-    }
-    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
-    FDTD_TRY(nccl_bind());
-    ncclUniqueId id;
-    NCCL_TRY(g_nccl.GetUniqueId(&id));
-    memcpy(id128, &id, sizeof id);
-    return FDTD_OK;
-}
-
-int fdtd_ctx_comm_init(fdtd_ctx *c, const void *id128)
-{
-    FDTD_TRY(check_ctx(c, "fdtd_ctx_comm_init"));
-    if (!id128) {
-        fdtd_set_error("fdtd_ctx_comm_init: NULL id");
-        return FDTD_E_ARG;
-    }
-    if (c->has_comm) {
-        fdtd_set_error("fdtd_ctx_comm_init: communicator already initialised");
-        return FDTD_E_STATE;
-    }
-    FDTD_TRY(use_device(c));
-    FDTD_TRY(nccl_bind());
-    ncclUniqueId id;
-    memcpy(&id, id128, sizeof id);
-    NCCL_TRY(g_nccl.CommInitRank(&c->comm, c->nranks, id, c->rank));
-    c->has_comm = true;
     return FDTD_OK;
 }
 
@@ -997,6 +850,8 @@ int fdtd_ctx_set_option(fdtd_ctx *c, const char *key, long value)
     else if (!strcmp(key, "warps_x") && value >= 1 && value <= 8) c->opt_wx = value;
     else if (!strcmp(key, "warps_y") && value >= 1 && value <= 8) c->opt_wy = value;
     else if (!strcmp(key, "prefetch") && value >= 0 && value <= 64) c->opt_prefetch = value;
+    else if (!strcmp(key, "host_chunk") && value >= 0 && value <= 1 << 20) c->opt_host_chunk = value;
+    else if (!strcmp(key, "host_pipeline") && value >= 0 && value <= 1) c->opt_host_pipeline = value;
     else {
         fdtd_set_error("fdtd_ctx_set_option: unknown key or bad value: %s = %ld", key, value);
         return FDTD_E_ARG;
@@ -1018,9 +873,14 @@ int fdtd_ctx_get_option(fdtd_ctx *c, const char *key, long *value)
     else if (!strcmp(key, "warps_y")) *value = c->opt_wy;
     else if (!strcmp(key, "prefetch")) *value = c->opt_prefetch;
     else if (!strcmp(key, "stages")) *value = c->opt_stages;
+    else if (!strcmp(key, "host_chunk")) *value = c->opt_host_chunk;
+    else if (!strcmp(key, "host_pipeline")) *value = c->opt_host_pipeline;
     else if (!strcmp(key, "k0")) *value = (long)c->k0;
     else if (!strcmp(key, "k1")) *value = (long)c->k1;
     else if (!strcmp(key, "launches")) *value = c->launches;
+    else if (!strcmp(key, "fallback")) *value = c->fallback;
+    else if (!strcmp(key, "transport")) *value = c->transport;
+    else if (!strcmp(key, "fused_ok")) *value = c->nranks == 1 ? (c->base2 != nullptr) : (c->fused_ok ? 1 : 0);
     else {
         fdtd_set_error("fdtd_ctx_get_option: unknown key %s", key);
         return FDTD_E_ARG;
@@ -1060,6 +920,7 @@ static int upload_impl(fdtd_ctx *c, const fdtd_fields *host, bool whole_cavity)
         return FDTD_E_ARG;
     }
     FDTD_TRY(use_device(c));
+    FDTD_TRY(wait_halos(c)); /* a neighbour may still be reading the planes this overwrites */
     double *h[6] = {host->Ex, host->Ey, host->Ez, host->Hx, host->Hy, host->Hz};
     for (int a = 0; a < 6; ++a)
         FDTD_TRY(copy_field(c, a, h[a] + slab_offset(c, a, whole_cavity), true));
@@ -1097,6 +958,8 @@ int fdtd_set_initial_conditions(fdtd_ctx *c)
     }
     int rc = fdtd_initial_conditions_planes(&c->p, c->k0, nplanes, ey);
     if (rc == FDTD_OK)
+        rc = wait_halos(c);
+    if (rc == FDTD_OK)
         rc = copy_field(c, 1, ey, true);
     if (rc == FDTD_OK && cudaStreamSynchronize(c->s_main) != cudaSuccess) {
         fdtd_set_error("fdtd_set_initial_conditions: upload failed");
@@ -1119,6 +982,7 @@ int fdtd_set_source(fdtd_ctx *c, double t)
         c->h_halo_valid = c->low_e_halo_valid = false; /* plane k = 0 may be a plane that travels (same on all ranks) */
     if (!c->src_here)
         return FDTD_OK; /* the patch lives on the slab that holds k = 0 */
+    FDTD_TRY(wait_halos(c));
     std::vector<double> row(2 * (size_t)c->src_n);
     FDTD_TRY(fdtd_source_values(&c->p, &c->plan, t, row.data(), row.data() + c->src_n));
     CUDA_TRY(cudaMemcpyAsync(c->src_one_dev, row.data(), row.size() * sizeof(double),
@@ -1133,7 +997,8 @@ int fdtd_update_H_field(fdtd_ctx *c)
 {
     FDTD_TRY(check_solo(c, "fdtd_update_H_field"));
     FDTD_TRY(use_device(c));
-    FDTD_TRY(refresh_halos(c));
+    FDTD_TRY(refresh_halos_many(&c, 1, false));
+    FDTD_TRY(wait_halos(c));
     launch_h(c, no_src(), 1, c->g.nk + c->g.top + 1, c->s_main);
     CUDA_TRY(cudaGetLastError());
     c->h_halo_valid = (c->nranks == 1);
@@ -1144,7 +1009,8 @@ int fdtd_update_E_field(fdtd_ctx *c)
 {
     FDTD_TRY(check_solo(c, "fdtd_update_E_field"));
     FDTD_TRY(use_device(c));
-    FDTD_TRY(refresh_halos(c));
+    FDTD_TRY(refresh_halos_many(&c, 1, false));
+    FDTD_TRY(wait_halos(c));
     launch_e(c, no_src(), 1, c->g.nk + 1, c->s_main);
     CUDA_TRY(cudaGetLastError());
     c->e_halo_valid = c->low_e_halo_valid = (c->nranks == 1);
@@ -1175,6 +1041,7 @@ int fdtd_sync(fdtd_ctx *c)
 {
     FDTD_TRY(check_ctx(c, "fdtd_sync"));
     FDTD_TRY(use_device(c));
+    FDTD_TRY(wait_halos(c)); /* also what the neighbours still push into this slab's halo planes */
     CUDA_TRY(cudaStreamSynchronize(c->s_main));
     CUDA_TRY(cudaStreamSynchronize(c->s_comm));
     CUDA_TRY(cudaStreamSynchronize(c->s_dump));

@@ -57,6 +57,7 @@ namespace fdtdi {
     ncclResult_t (*CommDestroy)(ncclComm_t);
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
     ncclResult_t (*GroupStart)(void);
     ncclResult_t (*GroupEnd)(void);
     const char *(*GetErrorString)(ncclResult_t);
@@ -66,6 +67,27 @@ extern NcclApi g_nccl;
 int nccl_bind();
 
 constexpr int kSrcRing = 512; /* source rows (steps) resident on the device at a time */
+
+/* How the halo planes travel between neighbouring slabs (fdtd_halo.cu):
+ *   TR_NCCL   ncclSend / ncclRecv on the halo stream (one process per GPU, or a group);
+ *   TR_EVENT  slabs of one fdtd_group: the receiver pulls the planes with a peer copy (copy engines, no
+ *             SM), ordered by CUDA events of the neighbour's streams -- also works when several slabs
+ *             share one device (tests on a 1-GPU box);
+ *   TR_FLAG   one process per GPU without NCCL: the sender pushes the planes into the neighbour's halo
+ *             planes, mapped through CUDA IPC, and raises a sequence flag in the neighbour's memory;
+ *             the streams wait on the flags (cuStreamWaitValue32). */
+enum Transport { TR_NONE = 0, TR_NCCL = 1, TR_EVENT = 2, TR_FLAG = 3 };
+
+/* flag words of TR_FLAG, 16 words apart */
+enum { SIG_UP_DATA = 0, SIG_DOWN_DATA = 16, SIG_UP_ACK = 32, SIG_DOWN_ACK = 48, SIG_SCRATCH = 64, SIG_WORDS = 96 };
+
+/* which planes an exchange moves */
+struct Xchg {
+    bool h;        /* Hx, Hy of my top cell plane -> plane 0 of rank+1 */
+    bool h_with_e; /*   ... and Ex, Ey, Ez of that plane (fused step) */
+    bool e;        /* Ex, Ey of my first node plane -> plane nk+1 of rank-1 */
+    bool e_with_hz;/*   ... and Hz (dump variables only) */
+};
 
 struct DumpPipe;
 
@@ -85,12 +107,28 @@ struct fdtd_ctx {
     double ch, ce;      /* update factors, main.c:441 / :479 */
 
     cudaStream_t s_main, s_comm, s_dump;
-    cudaEvent_t ev_hb, ev_eb, ev_hhalo, ev_ehalo;
+    cudaEvent_t ev_bnd;             /* compute stream: the planes my neighbours need are final, my halos are consumed */
+    cudaEvent_t ev_hhalo, ev_ehalo; /* halo stream: the last exchange of that kind has finished here */
+    cudaEvent_t ev_sent;            /* TR_FLAG: my pushes have left my planes */
     bool e_halo_valid, h_halo_valid;
     bool low_e_halo_valid; /* fused step only: plane 0 also holds the lower neighbour's Ex, Ey, Ez */
     ncclComm_t comm;
     bool has_comm;
     bool in_group;      /* slab of an fdtd_group: calls that exchange halos go through the group */
+    int transport;      /* fdtdi::Transport */
+    fdtd_ctx *nb_lo, *nb_hi;         /* TR_EVENT: the neighbouring slabs of the group */
+    double *peer_lo[2], *peer_hi[2]; /* TR_FLAG: the neighbours' two state sets; [flip] is their current one */
+    unsigned *peer_sig_lo, *peer_sig_hi;
+    int peer_nk_lo;                  /* cell planes of the lower neighbour (its upper halo is plane nk + 1) */
+    size_t peer_elems_lo, peer_elems_hi; /* elements per array over there (slabs may differ by one plane) */
+    void *ipc_mapped[6];
+    int n_ipc;
+    unsigned *sig;                   /* my flag words (device), SIG_WORDS of them */
+    unsigned n_xh, n_xe;             /* exchanges of each kind so far: the sequence numbers of TR_FLAG */
+    int flip;                        /* buffer swaps since the slabs were wired, modulo 2 */
+    bool wired;                      /* comm_init / peer_connect / group wiring done */
+    bool fused_ok;                   /* every slab holds the second state copy (agreed when wiring) */
+    int fallback;                    /* 1: the automatically chosen fused kernel was replaced by the split ones */
 
     /* source */
     fdtd_source_plan plan;
@@ -103,6 +141,8 @@ struct fdtd_ctx {
 
     /* options */
     long opt_kernel, opt_strip, opt_kchunk, opt_wx, opt_wy, opt_prefetch, opt_stages;
+    long opt_host_chunk, opt_host_pipeline; /* fdtd_run_hosted: planes per z-chunk (0 = automatic), 0/1 */
+    cudaStream_t s_h2d;                     /* uploads of fdtd_run_hosted (created on first use) */
 
     /* tensor maps of the TMA-staged fused step: [buffer set][array], valid for tma_bx x tma_by tiles */
     TmaMaps tma_maps[2];
@@ -139,21 +179,32 @@ struct DenseShape {
 DenseShape dense_shape(const fdtd_params &p, int idx);
 
 int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx **out);
+int copy_planes(fdtd_ctx *c, int idx, double *host_first_owned_plane, int kl0, int kl1, bool to_device, cudaStream_t st);
+int copy_field(fdtd_ctx *c, int idx, double *host_first_owned_plane, bool to_device);
+void launch_fused(fdtd_ctx *c, const fdtd::Src &s, int kl_begin, int kl_end, cudaStream_t st);
+void swap_buffers(fdtd_ctx *c);
+int settle_kernel(fdtd_ctx *c);
 int ensure_pong(fdtd_ctx *c);
 void fall_back_to_split(fdtd_ctx *c);
 fdtd::Src make_src(const fdtd_ctx *c, const double *row);
 int stage_source_rows(fdtd_ctx *c, size_t count, double *t_io);
 
-/* halo exchange: the NCCL calls only (may sit inside a caller's NCCL group) */
-int exchange_h(fdtd_ctx *c, cudaStream_t st, bool with_e);
-int exchange_e(fdtd_ctx *c, cudaStream_t st, bool with_hz);
-int join_halo_stream(fdtd_ctx *c);
+/* halo exchange (fdtd_halo.cu).  exchange_many moves the planes `x` names between the n slabs this
+ * thread drives (n = 1: one process per GPU); on_comm: on the halo streams, after each slab's ev_bnd
+ * (stepping) -- otherwise on the compute streams, in order with everything queued so far. */
+int exchange_many(fdtd_ctx *const *cs, int n, const Xchg &x, bool on_comm);
+/* the compute stream waits until the halos of the last exchanges have arrived and the planes they
+ * sent have been read: before any kernel that reads halo planes or overwrites owned ones */
+int wait_halos(fdtd_ctx *c);
+/* bring the halos the selected kernels need up to date (after uploads and operator-level calls) */
+int refresh_halos_many(fdtd_ctx *const *cs, int n, bool fused);
+void halo_destroy(fdtd_ctx *c);
+int alloc_sig(fdtd_ctx *c);
 
-/* the three parts of a step segment (see fdtd_ctx.cu) */
+/* a step is made of segments: one for the fused kernels, two for the split ones (see fdtd_ctx.cu) */
 enum Segment { SEG_FUSED, SEG_H, SEG_E };
 int seg_launch(fdtd_ctx *c, const fdtd::Src &s, Segment seg);
-int seg_exchange(fdtd_ctx *c, Segment seg);
-int seg_finish(fdtd_ctx *c, Segment seg);
+Xchg seg_xchg(Segment seg);
 
 /* one context, optionally timed (one process per GPU) */
 int run_impl(fdtd_ctx *c, size_t steps, double *time_counter, float *total_ms, float *h_ms, float *e_ms);

@@ -132,6 +132,7 @@ int fdtd_fill_test_pattern(fdtd_ctx *c, unsigned long long seed)
 {
     FDTD_TRY(check_ctx(c, "fdtd_fill_test_pattern"));
     FDTD_TRY(use_device(c));
+    FDTD_TRY(wait_halos(c)); /* nothing of the last exchange may still be in flight */
     CUDA_TRY(cudaMemsetAsync(c->base, 0, 6 * c->array_elems * sizeof(double), c->s_main));
     for (int a = 0; a < 6; ++a) {
         const DenseView v = dense_view(c, a);

@@ -2,14 +2,14 @@
  * fdtd_group.cu -- all z-slabs of a cavity driven by ONE host thread (fdtd_group_*).
  *
  * The reference is a single-threaded C program; this keeps its host program one: no MPI, no
- * launcher.  A group is n slab contexts, one per GPU of the box, with a NCCL communicator made by
- * ncclCommInitAll.  Every call only queues work; the slabs advance concurrently on their own
- * streams.  Because one thread issues the NCCL calls of all ranks, each exchange is wrapped in a
- * single NCCL group (otherwise rank 0's send would wait for a receive this thread has not posted
- * yet): that is what the three-part segments of fdtd_ctx.cu are for.
+ * launcher.  A group is n slab contexts, normally one per GPU of the box.  Every call only queues
+ * work; the slabs advance concurrently on their own streams.  Halo planes travel by peer copies
+ * ordered with CUDA events (TR_EVENT, fdtd_halo.cu) or, on request, by NCCL send/recv through a
+ * communicator made by ncclCommInitAll; because one thread issues the transfers of all slabs, every
+ * exchange is queued in phases over all slabs (exchange_many).
  *
- * The one-process-per-GPU route (fdtd_ctx_create_slab + fdtd_ctx_comm_init) runs the same segments
- * without the outer group.
+ * The one-process-per-GPU route (fdtd_ctx_create_slab + fdtd_ctx_comm_init / fdtd_ctx_peer_connect)
+ * runs the same segments for its one slab.
  */
 #include "fdtd_ctx.hpp"
 
@@ -23,39 +23,17 @@ struct fdtd_group {
 
 namespace fdtdi {
 
-/* NCCL group around a per-slab call */
-template <typename F>
-int grouped(fdtd_ctx *const *cs, int n, F &&per_slab)
-{
-    if (n > 1)
-        NCCL_TRY(g_nccl.GroupStart());
-    int rc = FDTD_OK;
-    for (int r = 0; r < n && rc == FDTD_OK; ++r)
-        rc = per_slab(cs[r]);
-    if (n > 1) {
-        ncclResult_t e = g_nccl.GroupEnd();
-        if (rc == FDTD_OK && e != ncclSuccess) {
-            fdtd_set_error("ncclGroupEnd: %s", g_nccl.GetErrorString(e));
-            rc = FDTD_E_NCCL;
-        }
-    }
-    return rc;
-}
-
 /* dumps read node plane k1 of Ex, Ey and Hz (main.c:517-520, 538-539) */
 int exchange_many_for_dump(fdtd_ctx *const *cs, int n)
 {
     if (cs[0]->nranks == 1)
         return FDTD_OK;
-    for (int r = 0; r < n; ++r) {
-        FDTD_TRY(use_device(cs[r]));
+    Xchg x;
+    x.h = x.h_with_e = false;
+    x.e = x.e_with_hz = true;
+    for (int r = 0; r < n; ++r)
         cs[r]->e_halo_valid = false;
-        FDTD_TRY(join_halo_stream(cs[r]));
-    }
-    FDTD_TRY(grouped(cs, n, [](fdtd_ctx *c) {
-        FDTD_TRY(use_device(c));
-        return exchange_e(c, c->s_main, true);
-    }));
+    FDTD_TRY(exchange_many(cs, n, x, false));
     for (int r = 0; r < n; ++r)
         cs[r]->e_halo_valid = true;
     return FDTD_OK;
@@ -76,38 +54,14 @@ static int group_run(fdtd_ctx *const *cs, int n, size_t steps, double *time_coun
                 return rc;
         }
         if (nomem) {
-            for (int r = 0; r < n; ++r)
+            for (int r = 0; r < n; ++r) {
+                FDTD_TRY(use_device(cs[r]));
                 fall_back_to_split(cs[r]);
+            }
             want_fused = false;
         }
     }
-    /* halos (the flags are identical on all slabs by construction) */
-    fdtd_ctx *c0 = cs[0];
-    const bool need_e = !c0->e_halo_valid;
-    const bool need_h = !c0->h_halo_valid || (want_fused && !c0->low_e_halo_valid);
-    if (need_e || need_h) {
-        for (int r = 0; r < n; ++r) {
-            FDTD_TRY(use_device(cs[r]));
-            FDTD_TRY(join_halo_stream(cs[r]));
-        }
-        FDTD_TRY(grouped(cs, n, [&](fdtd_ctx *c) {
-            FDTD_TRY(use_device(c));
-            if (need_e)
-                FDTD_TRY(exchange_e(c, c->s_main, false));
-            if (need_h)
-                FDTD_TRY(exchange_h(c, c->s_main, want_fused));
-            return (int)FDTD_OK;
-        }));
-        for (int r = 0; r < n; ++r) {
-            cs[r]->e_halo_valid = cs[r]->h_halo_valid = true;
-            cs[r]->low_e_halo_valid = want_fused;
-        }
-    }
-    for (int r = 0; r < n; ++r) { /* the first step's waits need recorded events */
-        FDTD_TRY(use_device(cs[r]));
-        CUDA_TRY(cudaEventRecord(cs[r]->ev_ehalo, cs[r]->s_main));
-        CUDA_TRY(cudaEventRecord(cs[r]->ev_hhalo, cs[r]->s_main));
-    }
+    FDTD_TRY(refresh_halos_many(cs, n, want_fused));
 
     const Segment fused_plan[1] = {SEG_FUSED}, split_plan[2] = {SEG_H, SEG_E};
     const Segment *plan = want_fused ? fused_plan : split_plan;
@@ -128,9 +82,7 @@ static int group_run(fdtd_ctx *const *cs, int n, size_t steps, double *time_coun
                     const fdtd::Src src = make_src(c, c->src_dev + s * 2 * (size_t)c->src_n);
                     FDTD_TRY(seg_launch(c, src, plan[g]));
                 }
-                FDTD_TRY(grouped(cs, n, [&](fdtd_ctx *c) { return seg_exchange(c, plan[g]); }));
-                for (int r = 0; r < n; ++r)
-                    FDTD_TRY(seg_finish(cs[r], plan[g]));
+                FDTD_TRY(exchange_many(cs, n, seg_xchg(plan[g]), true));
             }
         }
         t = t_chunk;
@@ -153,10 +105,12 @@ int step_many(fdtd_ctx *const *cs, int n, size_t steps, double *time_counter)
 
 extern "C" {
 
-int fdtd_group_create(const fdtd_params *p, int ngpus, const int *devices, fdtd_group **out)
+/* transport: 0 = peer copies ordered by events (TR_EVENT; the default, also for slabs that share a
+ * device), 1 = NCCL send/recv (needs one distinct GPU per slab) */
+int fdtd_group_create_transport(const fdtd_params *p, int ngpus, const int *devices, int transport, fdtd_group **out)
 {
-    if (!p || !out || ngpus < 1 || ngpus > 64) {
-        fdtd_set_error("fdtd_group_create: bad argument (ngpus %d)", ngpus);
+    if (!p || !out || ngpus < 1 || ngpus > 64 || transport < 0 || transport > 1) {
+        fdtd_set_error("fdtd_group_create: bad argument (ngpus %d, transport %d)", ngpus, transport);
         return FDTD_E_ARG;
     }
     fdtd_group *g = new (std::nothrow) fdtd_group();
@@ -174,7 +128,7 @@ int fdtd_group_create(const fdtd_params *p, int ngpus, const int *devices, fdtd_
         if (rc == FDTD_OK)
             g->ctx.push_back(c);
     }
-    if (rc == FDTD_OK && ngpus > 1) {
+    if (rc == FDTD_OK && ngpus > 1 && transport == 1) {
         rc = nccl_bind();
         if (rc == FDTD_OK) {
             std::vector<ncclComm_t> comms(ngpus);
@@ -186,11 +140,34 @@ int fdtd_group_create(const fdtd_params *p, int ngpus, const int *devices, fdtd_
                 for (int r = 0; r < ngpus; ++r) {
                     g->ctx[r]->comm = comms[r];
                     g->ctx[r]->has_comm = true;
-                    g->ctx[r]->in_group = true;
+                    g->ctx[r]->transport = TR_NCCL;
                 }
             }
         }
+    } else if (rc == FDTD_OK && ngpus > 1) {
+        for (int r = 0; r < ngpus; ++r) {
+            fdtd_ctx *c = g->ctx[r];
+            c->transport = TR_EVENT;
+            c->nb_lo = r > 0 ? g->ctx[r - 1] : nullptr;
+            c->nb_hi = r + 1 < ngpus ? g->ctx[r + 1] : nullptr;
+            /* direct NVLink copies where the devices can reach each other; otherwise the peer copy is
+             * staged by the driver */
+            for (fdtd_ctx *nb : {c->nb_lo, c->nb_hi}) {
+                if (!nb || nb->device == c->device)
+                    continue;
+                int can = 0;
+                if (cudaSetDevice(c->device) == cudaSuccess &&
+                    cudaDeviceCanAccessPeer(&can, c->device, nb->device) == cudaSuccess && can)
+                    cudaDeviceEnablePeerAccess(nb->device, 0);
+                cudaGetLastError(); /* "already enabled" is fine */
+            }
+        }
     }
+    if (rc == FDTD_OK)
+        for (fdtd_ctx *c : g->ctx) {
+            c->in_group = ngpus > 1;
+            c->wired = true;
+        }
     if (rc != FDTD_OK) {
         for (fdtd_ctx *c : g->ctx)
             fdtd_ctx_destroy(c);
@@ -201,10 +178,22 @@ int fdtd_group_create(const fdtd_params *p, int ngpus, const int *devices, fdtd_
     return FDTD_OK;
 }
 
+int fdtd_group_create(const fdtd_params *p, int ngpus, const int *devices, fdtd_group **out)
+{
+    const char *env = getenv("FDTD_B200_TRANSPORT");
+    return fdtd_group_create_transport(p, ngpus, devices, env && !strcmp(env, "nccl") ? 1 : 0, out);
+}
+
 int fdtd_group_destroy(fdtd_group *g)
 {
     if (!g)
         return FDTD_OK;
+    for (fdtd_ctx *c : g->ctx) /* a slab's streams may still wait on a neighbour's events */
+        fdtd_sync(c);
+    for (fdtd_ctx *c : g->ctx) {
+        c->wired = false; /* the neighbours are about to go away */
+        c->nb_lo = c->nb_hi = nullptr;
+    }
     for (fdtd_ctx *c : g->ctx)
         fdtd_ctx_destroy(c);
     delete g;

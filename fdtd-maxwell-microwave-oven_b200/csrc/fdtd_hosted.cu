@@ -1,0 +1,180 @@
+/*
+ * fdtd_hosted.cu -- fdtd_run_hosted: the stepping loop of main.c:765-779 for a caller whose fields
+ * live in HOST memory, like the reference's (its update functions mutate the host arrays in place).
+ *
+ * Done naively this is three phases in sequence -- upload 51.6 GB, step, download 51.6 GB at 1024^3 --
+ * and for a short run the PCIe copies are most of the time.  But a time step only couples a z-plane to
+ * its two neighbours, so the three phases can run as one wavefront over z-chunks:
+ *
+ *     step s of chunk c  needs  step s-1 of chunks c-1, c, c+1
+ *
+ * Chunks are uploaded bottom-up on a copy stream.  As soon as chunk u has landed, "wave" u runs on the
+ * compute stream: step 1 of chunk u-1, step 2 of chunk u-2, ... step s of chunk u-s.  When step K of a
+ * chunk is done, that chunk goes back to the host on a third stream -- the other PCIe direction --
+ * while higher chunks are still arriving.  The download thus trails the upload by only K chunks and
+ * the whole call takes about one upload time instead of upload + K steps + download.
+ *
+ * Hazards.  The fused step reads one buffer set and writes the other (fdtd_fused_tma.cuh): step s
+ * reads X[s-1] and writes X[s], and X[s] shares its memory with X[s-2].  Within a wave the launches
+ * are queued in the order s = 1, 2, ...: (s-1, c+1) -- the last reader of what (s, c) overwrites, and
+ * the last producer of what it reads -- is the launch queued right before (s, c), and everything
+ * else it depends on belongs to earlier waves of the same in-order stream.
+ *
+ * The arithmetic per element is untouched, so the result is bit-identical to upload + fdtd_run +
+ * download (tests/test_gpu_hosted.py).  Long runs use the wavefront only to ramp in (first steps,
+ * during the upload) and to ramp out (last steps, during the download); the steps in between run as
+ * whole-grid launches.  Multi-slab contexts and the in-place kernels (0, 1) take the plain sequence.
+ */
+#include "fdtd_ctx.hpp"
+
+using namespace fdtdi;
+
+namespace fdtdi {
+
+struct Chunks {
+    int planes;              /* local planes 1 .. planes are swept (nk + 1 on the last slab) */
+    int size, count;
+    int begin(int c) const { return 1 + c * size; }
+    int end(int c) const { return std::min(1 + (c + 1) * size, planes + 1); }
+};
+
+static double *host_array(const fdtd_fields *h, int idx)
+{
+    double *a[6] = {h->Ex, h->Ey, h->Ez, h->Hx, h->Hy, h->Hz};
+    return a[idx];
+}
+
+/* steps [s_first, s_last] (1-based, of this call) as a wavefront; the state before step s_first is
+ * c->f.  upload: chunk u's planes arrive from `host` first (then s_first must be 1);
+ * download: each chunk leaves for `host` after its step s_last.  On return c->f is the final state. */
+static int wavefront(fdtd_ctx *c, const fdtd_fields *host, const Chunks &ch, int nsteps, bool upload, bool download,
+                     const double *src_rows)
+{
+    const int M = ch.count;
+    const size_t row = 2 * (size_t)c->src_n;
+    std::vector<cudaEvent_t> ev_up(upload ? M : 0), ev_done(download ? M : 0);
+    for (auto &e : ev_up)
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : ev_done)
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    int rc = FDTD_OK;
+    if (upload) {
+        /* the uploads overwrite the current set: everything queued so far must have finished with it */
+        cudaEvent_t ev0 = ev_up[0];
+        CUDA_TRY(cudaEventRecord(ev0, c->s_main));
+        CUDA_TRY(cudaStreamWaitEvent(c->s_h2d, ev0, 0));
+        for (int u = 0; u < M && rc == FDTD_OK; ++u) {
+            for (int a = 0; a < 6 && rc == FDTD_OK; ++a)
+                rc = copy_planes(c, a, host_array(host, a), ch.begin(u), ch.end(u), true, c->s_h2d);
+            if (rc == FDTD_OK && cudaEventRecord(ev_up[u], c->s_h2d) != cudaSuccess)
+                rc = FDTD_E_CUDA;
+        }
+    }
+    /* X[0] is the current set; parity p: is c->f currently X[even] (0) or X[odd] (1)? */
+    int parity = 0;
+    for (int u = 1; u <= M - 1 + nsteps && rc == FDTD_OK; ++u) {
+        /* step 1 of chunk u-1 reads chunks u-2 .. u: the copy stream is in order, so one event does */
+        if (upload && u <= M)
+            CUDA_TRY(cudaStreamWaitEvent(c->s_main, ev_up[std::min(u, M - 1)], 0));
+        for (int s = std::max(1, u - M + 1); s <= std::min(nsteps, u); ++s) {
+            const int k = u - s; /* chunk */
+            if (((s - 1) & 1) != parity) { /* step s reads X[s-1] */
+                swap_buffers(c);
+                parity ^= 1;
+            }
+            launch_fused(c, make_src(c, src_rows + (size_t)(s - 1) * row), ch.begin(k), ch.end(k), c->s_main);
+            if (c->launch_error != FDTD_OK) {
+                rc = c->launch_error;
+                c->launch_error = FDTD_OK;
+                break;
+            }
+            if (s == nsteps && download) {
+                /* chunk k is final: it lives in the set step nsteps wrote, i.e. c->f2 right now */
+                if (cudaEventRecord(ev_done[k], c->s_main) != cudaSuccess ||
+                    cudaStreamWaitEvent(c->s_dump, ev_done[k], 0) != cudaSuccess) {
+                    rc = FDTD_E_CUDA;
+                    break;
+                }
+                swap_buffers(c); /* copy_planes reads c->f */
+                for (int a = 0; a < 6 && rc == FDTD_OK; ++a)
+                    rc = copy_planes(c, a, host_array(host, a), ch.begin(k), ch.end(k), false, c->s_dump);
+                swap_buffers(c);
+            }
+        }
+    }
+    if (rc == FDTD_OK && cudaGetLastError() != cudaSuccess)
+        rc = FDTD_E_CUDA;
+    /* make c->f the final state X[nsteps] */
+    if ((nsteps & 1) != parity)
+        swap_buffers(c);
+    if (rc == FDTD_OK && download) {
+        /* later work on the compute stream must not overwrite what is still leaving */
+        cudaEvent_t e = ev_done[0];
+        if (cudaEventRecord(e, c->s_dump) != cudaSuccess || cudaStreamWaitEvent(c->s_main, e, 0) != cudaSuccess)
+            rc = FDTD_E_CUDA;
+    }
+    for (auto &e : ev_up)
+        cudaEventDestroy(e);
+    for (auto &e : ev_done)
+        cudaEventDestroy(e);
+    if (rc == FDTD_E_CUDA)
+        fdtd_set_error("fdtd_run_hosted: %s", cudaGetErrorString(cudaGetLastError()));
+    return rc;
+}
+
+} /* namespace fdtdi */
+
+extern "C" {
+
+int fdtd_run_hosted(fdtd_ctx *c, const fdtd_fields *host, size_t steps, double *time_counter)
+{
+    FDTD_TRY(check_solo(c, "fdtd_run_hosted"));
+    if (!host || !host->Ex || !host->Ey || !host->Ez || !host->Hx || !host->Hy || !host->Hz || !time_counter) {
+        fdtd_set_error("fdtd_run_hosted: NULL argument");
+        return FDTD_E_ARG;
+    }
+    FDTD_TRY(use_device(c));
+    FDTD_TRY(settle_kernel(c));
+    const int kWave = 32; /* steps ramped in / out as a wavefront in a long run */
+    const bool pipelined = c->opt_host_pipeline && c->nranks == 1 && c->opt_kernel >= 2 && steps >= 1 &&
+                           steps <= (size_t)1 << 30;
+    if (!pipelined) {
+        FDTD_TRY(fdtd_upload_slab(c, host));
+        FDTD_TRY(run_impl(c, steps, time_counter, nullptr, nullptr, nullptr));
+        return fdtd_download_slab(c, host);
+    }
+    if (!c->s_h2d)
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    Chunks ch;
+    ch.planes = c->g.nk + c->g.top;
+    /* 8 planes per chunk keep the download close behind the upload; at most 256 chunks */
+    ch.size = c->opt_host_chunk > 0 ? (int)c->opt_host_chunk : std::max(8, (ch.planes + 255) / 256);
+    ch.size = std::max(ch.size, 2);
+    ch.count = (ch.planes + ch.size - 1) / ch.size;
+
+    double t = *time_counter;
+    auto stage = [&](size_t count) { /* source rows of the next `count` steps -> c->src_dev */
+        return stage_source_rows(c, count, &t);
+    };
+    int rc;
+    if (steps <= 2 * (size_t)kWave) {
+        FDTD_TRY(stage(steps));
+        rc = wavefront(c, host, ch, (int)steps, true, true, c->src_dev);
+    } else {
+        FDTD_TRY(stage(kWave));
+        rc = wavefront(c, host, ch, kWave, true, false, c->src_dev);
+        if (rc == FDTD_OK)
+            rc = run_impl(c, steps - 2 * kWave, &t, nullptr, nullptr, nullptr);
+        if (rc == FDTD_OK)
+            rc = stage(kWave);
+        if (rc == FDTD_OK)
+            rc = wavefront(c, host, ch, kWave, false, true, c->src_dev);
+    }
+    FDTD_TRY(rc);
+    CUDA_TRY(cudaStreamSynchronize(c->s_dump));
+    CUDA_TRY(cudaStreamSynchronize(c->s_main));
+    *time_counter = t;
+    return FDTD_OK;
+}
+
+} /* extern "C" */

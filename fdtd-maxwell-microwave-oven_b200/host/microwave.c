@@ -14,8 +14,9 @@
  * if it does not, the run fails with the reference's message "Could not create DB".
  *
  * Environment: FDTD_B200_DEVICE (CUDA device index, default 0), FDTD_B200_GPUS=N (split the cavity
- * into N z-slabs on GPUs 0..N-1 of this box; still one process, one thread: fdtd_group_*; every
- * slab writes its own brick r/result%04d.slab<r>.raw whose BOV header carries the z origin),
+ * into N z-slabs on GPUs 0..N-1 of this box, or on the devices FDTD_B200_DEVICES=a,b,... names; still
+ * one process, one thread: fdtd_group_*; every slab writes its own brick r/result%04d.slab<r>.raw
+ * whose BOV header carries the z origin),
  * FDTD_B200_NO_DUMPS=1 (step without writing anything), FDTD_B200_REPORT=1 (timing summary on stderr).
  */
 #define _POSIX_C_SOURCE 199309L
@@ -131,7 +132,9 @@ int main(int argc, const char *argv[])
     const char *gpus_env = getenv("FDTD_B200_GPUS");
     const char *no_dumps = getenv("FDTD_B200_NO_DUMPS");
     const char *report = getenv("FDTD_B200_REPORT");
+    const char *devs_env = getenv("FDTD_B200_DEVICES");
     const int ngpus = gpus_env ? atoi(gpus_env) : 1;
+    int devices[64];
     int rc, r;
 
     printf("Welcome into our microwave oven eletrico-magnetic field simulator! \n");
@@ -153,8 +156,19 @@ int main(int argc, const char *argv[])
         fprintf(stderr, "FDTD_B200_GPUS must be between 1 and 64\n");
         return EXIT_FAILURE;
     }
+    for (r = 0; r < 64; ++r)
+        devices[r] = r;
+    if (devs_env) { /* comma-separated device index per slab; indices may repeat */
+        const char *q = devs_env;
+        for (r = 0; r < 64 && *q; ++r) {
+            devices[r] = atoi(q);
+            q += strcspn(q, ",");
+            if (*q == ',')
+                ++q;
+        }
+    }
     if (ngpus > 1) {
-        if (fdtd_group_create(&params, ngpus, NULL, &group) != FDTD_OK)
+        if (fdtd_group_create(&params, ngpus, devices, &group) != FDTD_OK)
             fail_lib("initialize_fields");
     } else if (fdtd_ctx_create(&params, dev_env ? atoi(dev_env) : 0, &ctx) != FDTD_OK) {
         fail_lib("initialize_fields");

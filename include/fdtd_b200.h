@@ -102,14 +102,38 @@ int fdtd_ctx_create(const fdtd_params *p, int device, fdtd_ctx **out);
 int fdtd_ctx_create_slab(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx **out);
 int fdtd_ctx_destroy(fdtd_ctx *ctx);
 
-/* NCCL bootstrap: rank 0 makes a 128-byte id, the host program distributes it (MPI, torchrun's
- * store, a file ...), every rank then joins. */
+/* Wiring the slabs of a one-process-per-GPU run to their neighbours.  Two ways, pick one, on every rank:
+ *
+ * (1) NCCL: rank 0 makes a 128-byte id, the host program distributes it (MPI, torchrun's store, a
+ *     file ...), every rank then joins; halo planes travel with ncclSend / ncclRecv.
+ * (2) Peer memory (one box): every rank exports a descriptor of its state (CUDA IPC handles), the host
+ *     program gathers the descriptors of ALL ranks, in rank order, and hands the table to every rank;
+ *     halo planes are then written straight into the neighbour's HBM over NVLink by the copy engines,
+ *     ordered by sequence flags the streams wait on -- no NCCL, no proxy kernels on the SMs.  Ranks may
+ *     share a device (that is how the slab logic is tested on a 1-GPU box).
+ *
+ * Both also agree, across all ranks, on whether the fused kernels can be used (they need the state
+ * twice in HBM on every slab): select the "kernel" option BEFORE wiring. */
 int fdtd_nccl_unique_id(void *id128);
 int fdtd_ctx_comm_init(fdtd_ctx *ctx, const void *id128);
+#define FDTD_PEER_BLOB_BYTES 384
+int fdtd_ctx_peer_export(fdtd_ctx *ctx, void *blob /* FDTD_PEER_BLOB_BYTES */);
+int fdtd_ctx_peer_connect(fdtd_ctx *ctx, const void *blobs /* nranks x FDTD_PEER_BLOB_BYTES, rank order */);
 
-/* Tunables: "kernel" (0 = one thread per cell, 1 = z-marching register strips),
- * "strip" rows per thread, "kchunk" planes per block, "warps_x", "warps_y".
- * Read-only: "k0", "k1" (owned cell planes), "launches" (kernels launched by this library). */
+/* Tunables.
+ *   "kernel"   0 = one thread per cell (the plain operators, source as separate launches);
+ *              1 = z-marching register strips, one H and one E launch per step, in place;
+ *              2 = H and E fused into one sweep per step (needs the state twice in HBM);
+ *              3 = the same sweep with operands staged by TMA into a shared-memory ring (default);
+ *              Left at its default the context falls back to kernel 1 -- with a line on stderr and
+ *              "fallback" = 1 -- when the second copy of the state does not fit; a kernel chosen
+ *              explicitly fails with FDTD_E_NOMEM instead.
+ *   "strip"    rows per thread (1..4);  "kchunk" planes per block;  "warps_x", "warps_y" block shape in
+ *              warps (at most 8 warps; 16 for kernel 3);  "stages" depth of the TMA ring (2..8, kernel 3);
+ *              "prefetch" planes of L2 prefetch ahead of the sweep (kernel 2).
+ * Read-only: "k0", "k1" (owned cell planes), "launches" (kernels launched by this library so far),
+ *   "fallback" (1 after the automatic fallback), "fused_ok" (second state copy available on every slab),
+ *   "transport" (0 none, 1 NCCL, 2 peer copies of a group, 3 peer memory with flags). */
 int fdtd_ctx_set_option(fdtd_ctx *ctx, const char *key, long value);
 int fdtd_ctx_get_option(fdtd_ctx *ctx, const char *key, long *value);
 
@@ -140,6 +164,16 @@ int fdtd_run(fdtd_ctx *ctx, size_t steps, double *time_counter);
 int fdtd_run_timed(fdtd_ctx *ctx, size_t steps, double *time_counter, float *total_ms,
                    float *h_ms, float *e_ms);
 int fdtd_sync(fdtd_ctx *ctx);
+/* The same loop for a caller whose fields live in HOST memory, as the reference's do (its update
+ * functions mutate the host arrays in place, main.c:431-500): `host` holds this slab's planes in the
+ * reference's dense layout (as for fdtd_upload_slab) and is advanced in place by `steps` passes.
+ * On a single-slab context with the fused kernels the upload, the stepping and the download run as one
+ * wavefront over z-chunks (chunk c of step s only needs chunks c-1, c, c+1 of step s-1), so the two
+ * PCIe directions and the kernels overlap; results are bit-identical to fdtd_upload_slab + fdtd_run +
+ * fdtd_download_slab, which is also what other contexts do.  Use pinned arrays (fdtd_host_alloc).
+ * Options: "host_chunk" planes per z-chunk (0 = automatic), "host_pipeline" 0 = always in sequence.
+ * Blocks until the host arrays hold the result. */
+int fdtd_run_hosted(fdtd_ctx *ctx, const fdtd_fields *host, size_t steps, double *time_counter);
 
 /* Dump variables of write_silo(), main.c:563-579: zone-centred averages with the reference's
  * operand order.  var: 0 ex, 1 ey, 2 ez, 3 hx, 4 hy, 5 hz.  host_out: maxi*maxj*nk doubles for the
@@ -182,11 +216,15 @@ int fdtd_host_free(void *ptr);
  * stay accessible (fdtd_group_ctx) for calls that touch one slab only (fdtd_upload_slab,
  * fdtd_download_slab, fdtd_checksum, fdtd_validation_error, fdtd_ctx_info); calls that exchange halos
  * (stepping, fdtd_aggregate, fdtd_energy, fdtd_propagate) must go through the group, because one
- * thread has to post every slab's sends and receives inside one NCCL group -- on a slab of a group
- * they return FDTD_E_STATE.
+ * thread has to queue every slab's transfers together -- on a slab of a group they return
+ * FDTD_E_STATE.
  * devices: ngpus CUDA device indices, or NULL for 0 .. ngpus-1. */
 typedef struct fdtd_group fdtd_group;
 int fdtd_group_create(const fdtd_params *p, int ngpus, const int *devices, fdtd_group **out);
+/* transport 0: peer copies over NVLink ordered by CUDA events (the default of fdtd_group_create; slabs
+ * may share a device); 1: NCCL send/recv (also selected by FDTD_B200_TRANSPORT=nccl in the environment) */
+int fdtd_group_create_transport(const fdtd_params *p, int ngpus, const int *devices, int transport,
+                                fdtd_group **out);
 int fdtd_group_destroy(fdtd_group *group);
 int fdtd_group_size(fdtd_group *group);
 int fdtd_group_ctx(fdtd_group *group, int rank, fdtd_ctx **out);

@@ -1,6 +1,8 @@
-"""z-slab decomposition on real GPUs (one process per GPU, NCCL halos): every slab's planes must
-equal the single-domain oracle bit for bit, for the operator-level calls, for fdtd_run (halo
-traffic overlapped with the interior planes) and for the dump variables.  Skipped on a 1-GPU box."""
+"""z-slab decomposition with one process per slab: every slab's planes must equal the single-domain
+oracle bit for bit, for the operator-level calls, for fdtd_run (halo traffic overlapped with the
+interior planes) and for the dump variables.  Two ways of wiring the slabs are covered: peer memory
+(CUDA IPC + sequence flags, fdtd_ctx_peer_connect) -- which also works when the slabs share one GPU,
+so these tests run on a 1-GPU box -- and NCCL (fdtd_ctx_comm_init), which needs one GPU per slab."""
 import os
 import socket
 
@@ -20,7 +22,18 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, dims, mode, steps, variant, ret):
+def _wire(F, dist, ctx, rank, world, transport):
+    if transport == "nccl":
+        box = [F.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(box[0])
+    else:
+        blobs = [None] * world
+        dist.all_gather_object(blobs, ctx.peer_export())
+        ctx.peer_connect(blobs)
+
+
+def _worker(rank, world, port, transport, cases, ret):
     import sys
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
@@ -29,61 +42,67 @@ def _worker(rank, world, port, dims, mode, steps, variant, ret):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        torch.cuda.set_device(rank)
-        nx, ny, nz = dims
-        args = ((nx + .5) * DX, (ny + .5) * DX, (nz + .5) * DX, DX, DT, 1e-9, 1, mode)
-        q, p = O.make_params(*args), F.make_params(*args)
-        assert q.dims() == dims == p.dims()
+        device = rank % torch.cuda.device_count()
+        torch.cuda.set_device(device)
         o = O.restatement()
-        f = O.alloc_fields(*dims, rng=np.random.default_rng(5))
-        init = {k[0].upper() + k[1:]: v.copy() for k, v in f.items()}
         bad = []
+        for case, (dims, mode, steps, variant) in enumerate(cases):
+            if world > dims[2]:
+                continue
+            nx, ny, nz = dims
+            args = ((nx + .5) * DX, (ny + .5) * DX, (nz + .5) * DX, DX, DT, 1e-9, 1, mode)
+            q, p = O.make_params(*args), F.make_params(*args)
+            assert q.dims() == dims == p.dims()
+            f = O.alloc_fields(*dims, rng=np.random.default_rng(5))
+            init = {k[0].upper() + k[1:]: v.copy() for k, v in f.items()}
 
-        def compare(ctx, what):
-            got = ctx.download({k: np.zeros_like(v) for k, v in init.items()})
-            k0, k1 = ctx.k0, ctx.k1
-            top = 1 if rank == world - 1 else 0
-            for name in ("Ez", "Hx", "Hy"):
-                if not np.array_equal(got[name][k0:k1].view(np.uint64), f[name.lower()][k0:k1].view(np.uint64)):
-                    bad.append((what, name))
-            for name in ("Ex", "Ey", "Hz"):
-                if not np.array_equal(got[name][k0:k1 + top].view(np.uint64),
-                                      f[name.lower()][k0:k1 + top].view(np.uint64)):
-                    bad.append((what, name))
+            def compare(ctx, what):
+                got = ctx.download({k: np.zeros_like(v) for k, v in init.items()})
+                k0, k1 = ctx.k0, ctx.k1
+                top = 1 if rank == world - 1 else 0
+                for name in ("Ez", "Hx", "Hy"):
+                    if not np.array_equal(got[name][k0:k1].view(np.uint64), f[name.lower()][k0:k1].view(np.uint64)):
+                        bad.append((case, what, name))
+                for name in ("Ex", "Ey", "Hz"):
+                    if not np.array_equal(got[name][k0:k1 + top].view(np.uint64),
+                                          f[name.lower()][k0:k1 + top].view(np.uint64)):
+                        bad.append((case, what, name))
 
-        with F.Context(p, device=rank, rank=rank, nranks=world) as ctx:
-            for k, v in variant.items():
-                ctx.set_option(k, v)
-            box = [F.nccl_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(box, src=0)
-            ctx.comm_init(box[0])
-            ctx.upload(init)
-            # operator level, like the reference's loop body
-            t = 0.0
-            for _ in range(2):
-                if mode == 1:
-                    ctx.set_source(t); o.set_source(q, f, t)
-                ctx.update_H_field(); o.update_h(q, f)
-                if mode == 1:
-                    ctx.set_source(t); o.set_source(q, f, t)
-                ctx.update_E_field(); o.update_e(q, f)
-                t += DT
-            compare(ctx, "operators")
-            # fused / overlapped path
-            t2 = ctx.run(steps, t)
-            t3 = o.run(q, f, steps, t)
-            assert t2 == t3
-            compare(ctx, "run")
-            for v in range(6):
-                want = o.aggregate(q, f, v)[ctx.k0:ctx.k1]
-                if not np.array_equal(ctx.aggregate(v).view(np.uint64), want.view(np.uint64)):
-                    bad.append(("aggregate", v))
-            sums = ctx.checksum()
-        allsums = [None] * world
-        dist.all_gather_object(allsums, sums)
-        total = [sum(s[a] for s in allsums) % (1 << 64) for a in range(6)]
-        if total != F.checksum_host({k[0].upper() + k[1:]: v for k, v in f.items()}):
-            bad.append(("checksum", total))
+            with F.Context(p, device=device, rank=rank, nranks=world) as ctx:
+                for k, v in variant.items():
+                    ctx.set_option(k, v)
+                _wire(F, dist, ctx, rank, world, transport)
+                assert ctx.get_option("transport") == (1 if transport == "nccl" else 3)
+                ctx.upload(init)
+                # operator level, like the reference's loop body
+                t = 0.0
+                for _ in range(2):
+                    if mode == 1:
+                        ctx.set_source(t); o.set_source(q, f, t)
+                    ctx.update_H_field(); o.update_h(q, f)
+                    if mode == 1:
+                        ctx.set_source(t); o.set_source(q, f, t)
+                    ctx.update_E_field(); o.update_e(q, f)
+                    t += DT
+                compare(ctx, "operators")
+                # fused / overlapped path, queued as several runs without a sync in between
+                t2 = ctx.run(steps - 2, t)
+                t2 = ctx.run(1, t2)
+                t2 = ctx.run(1, t2)
+                t3 = o.run(q, f, steps, t)
+                assert t2 == t3
+                compare(ctx, "run")
+                for v in range(6):
+                    want = o.aggregate(q, f, v)[ctx.k0:ctx.k1]
+                    if not np.array_equal(ctx.aggregate(v).view(np.uint64), want.view(np.uint64)):
+                        bad.append((case, "aggregate", v))
+                sums = ctx.checksum()
+                dist.barrier()   # nobody unmaps a neighbour's memory while it may still be written
+            allsums = [None] * world
+            dist.all_gather_object(allsums, sums)
+            total = [sum(s[a] for s in allsums) % (1 << 64) for a in range(6)]
+            if total != F.checksum_host({k[0].upper() + k[1:]: v for k, v in f.items()}):
+                bad.append((case, "checksum", total))
         ret[rank] = bad
     finally:
         dist.destroy_process_group()
@@ -98,36 +117,41 @@ CASES = [((37, 28, 23), 1, 7, dict(kernel=1, strip=2, kchunk=8, warps_x=2, warps
          ((70, 21, 8), 1, 6, dict(kernel=2, strip=1, kchunk=100, warps_x=4, warps_y=1)),
          ((40, 33, 4), 1, 5, dict(kernel=2, strip=4, kchunk=16, warps_x=1, warps_y=2)),
          ((37, 28, 23), 1, 7, dict(kernel=3, strip=2, kchunk=8, warps_x=2, warps_y=2, stages=3)),
-         ((70, 21, 8), 0, 6, dict(kernel=3, strip=1, kchunk=100, warps_x=1, warps_y=4, stages=4))]
+         ((70, 21, 8), 0, 6, dict(kernel=3, strip=1, kchunk=100, warps_x=1, warps_y=4, stages=4)),
+         ((64, 21, 11), 1, 6, dict())]      # defaults; the last block in x holds the single column i = I
 
 
 if os.environ.get("FDTD_MULTI_QUICK") == "1":  # a short list for expensive many-GPU boxes
     CASES = [CASES[0], CASES[4], CASES[8], CASES[9]]
 
 
-@pytest.mark.parametrize("dims,mode,steps,variant", CASES)
-def test_slabs_match_single_domain(dims, mode, steps, variant):
-    ngpu = torch.cuda.device_count()
-    if ngpu < 2:
-        pytest.skip("needs at least 2 GPUs")
+def _spawn(target, world, *args):
     import torch.multiprocessing as mp
-    for world in sorted({2, min(ngpu, 4), min(ngpu, 8)}):
-        if world > dims[2]:
-            continue
-        ctx = mp.get_context("spawn")
-        ret = ctx.Manager().dict()
-        port = _free_port()
-        procs = [ctx.Process(target=_worker, args=(r, world, port, dims, mode, steps, variant, ret))
-                 for r in range(world)]
-        for pr in procs:
-            pr.start()
-        for pr in procs:
-            pr.join(timeout=300)
-            assert pr.exitcode == 0
-        assert dict(ret) == {r: [] for r in range(world)}, f"world={world}"
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=target, args=(r, world, port) + args + (ret,)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(timeout=600)
+        assert pr.exitcode == 0
+    return dict(ret)
 
 
-def _propagate_worker(rank, world, port, nums, ret):
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_slabs_match_single_domain(world, transport):
+    """all CASES in one set of `world` processes (spawning costs more than the cases)"""
+    ngpu = torch.cuda.device_count()
+    if transport == "nccl" and ngpu < world:
+        pytest.skip("NCCL needs one GPU per slab")
+    if transport == "peer" and world == 8 and ngpu < 8:
+        pytest.skip("8 slabs only where 8 GPUs exist")
+    assert _spawn(_worker, world, transport, CASES) == {r: [] for r in range(world)}, f"world={world}"
+
+
+def _propagate_worker(rank, world, port, transport, nums, ret):
     import sys
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
@@ -136,7 +160,8 @@ def _propagate_worker(rank, world, port, nums, ret):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        torch.cuda.set_device(rank)
+        device = rank % torch.cuda.device_count()
+        torch.cuda.set_device(device)
         path = f"/tmp/fdtd_multi_prop_{os.getpid()}.txt"
         O.write_params(path, nums)
         p, q = F.load_parameters(path), O.restatement().load_parameters(path)
@@ -145,15 +170,14 @@ def _propagate_worker(rank, world, port, nums, ret):
         if q.mode == 0:
             o.set_initial_conditions(q, f)
         got = []
-        with F.Context(p, device=rank, rank=rank, nranks=world) as ctx:
-            box = [F.nccl_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(box, src=0)
-            ctx.comm_init(box[0])
+        with F.Context(p, device=device, rank=rank, nranks=world) as ctx:
+            _wire(F, dist, ctx, rank, world, transport)
             if q.mode == 0:
                 ctx.set_initial_conditions()
             steps, _ = ctx.propagate(on_begin=lambda it, dims, k0: got.append({"it": it, "dims": dims, "k0": k0, "vars": {}}),
                                      on_variable=lambda name, arr: got[-1]["vars"].__setitem__(name, arr))
             k0, k1 = ctx.k0, ctx.k1
+            dist.barrier()
         nx, ny, nz = q.dims()
         names = ["ex", "ey", "ez", "hx", "hy", "hz"]
 
@@ -189,22 +213,13 @@ def _propagate_worker(rank, world, port, nums, ret):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
 @pytest.mark.parametrize("mode", [0, 1])
-def test_slab_propagate_dumps_match_oracle(mode):
+def test_slab_propagate_dumps_match_oracle(mode, transport):
     """fdtd_propagate on slabs: every rank dumps its own planes, same cadence, same contents
     (incl. the zone plane that averages with the upper neighbour's node plane, and aEy)."""
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs at least 2 GPUs")
-    import torch.multiprocessing as mp
+    world = 2 if transport == "nccl" else 3
+    if transport == "nccl" and torch.cuda.device_count() < world:
+        pytest.skip("NCCL needs one GPU per slab")
     nums = ("0.021", "0.017", "0.013", "0.001", "0.0000000000006", "0.000000000012", "4", str(mode))
-    world = 2
-    ctx = mp.get_context("spawn")
-    ret = ctx.Manager().dict()
-    port = _free_port()
-    procs = [ctx.Process(target=_propagate_worker, args=(r, world, port, nums, ret)) for r in range(world)]
-    for pr in procs:
-        pr.start()
-    for pr in procs:
-        pr.join(timeout=300)
-        assert pr.exitcode == 0
-    assert dict(ret) == {r: [] for r in range(world)}
+    assert _spawn(_propagate_worker, world, transport, nums) == {r: [] for r in range(world)}
