@@ -100,7 +100,8 @@ int copy_field(fdtd_ctx *c, int idx, double *host_first_owned_plane, bool to_dev
 Src make_src(const fdtd_ctx *c, const double *row)
 {
     Src s;
-    s.on = c->src_here ? 1 : 0;
+    s.on = c->src_plane >= 0 ? 1 : 0;
+    s.kl = c->src_plane;
     s.i0 = (int)c->plan.i0;
     s.i1 = (int)c->plan.i1;
     s.j0 = (int)c->plan.j0;
@@ -503,11 +504,11 @@ int stage_source_rows(fdtd_ctx *c, size_t count, double *t_io)
     CUDA_TRY(cudaEventSynchronize(c->ev_src)); /* previous upload has left the pinned buffer */
     double t = *t_io;
     for (size_t s = 0; s < count; ++s, t += c->p.time_step) {
-        if (c->src_here)
+        if (c->src_plane >= 0)
             FDTD_TRY(fdtd_source_values(&c->p, &c->plan, t, c->src_host + s * row,
                                         c->src_host + s * row + c->src_n));
     }
-    if (c->src_here && row > 0) {
+    if (c->src_plane >= 0 && row > 0) {
         CUDA_TRY(cudaMemcpyAsync(c->src_dev, c->src_host, count * row * sizeof(double),
                                  cudaMemcpyHostToDevice, c->s_main));
         CUDA_TRY(cudaEventRecord(c->ev_src, c->s_main));
@@ -727,6 +728,7 @@ int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx
     }
     c->src_n = 0;
     c->src_here = false;
+    c->src_plane = -1;
     if (p->mode == 1) {
         /* the reference writes the patch without a bounds check (main.c:745-752); outside the
          * grid that is undefined behaviour there and an error here */
@@ -739,6 +741,7 @@ int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx
         }
         c->src_n = (int)(c->plan.i1 - c->plan.i0);
         c->src_here = (c->k0 == 0);
+        c->src_plane = c->k0 == 0 ? 1 : (c->k0 == 1 ? 0 : -1);
     }
 
 #define CREATE_TRY(expr)                                                                       \

@@ -134,6 +134,7 @@ struct fdtd_ctx {
     fdtd_source_plan plan;
     int src_n;          /* points per row */
     bool src_here;      /* computation mode and this slab holds k = 0 */
+    int src_plane;      /* local index of the global plane k = 0 if a kernel of this slab touches it, else -1 */
     double *src_dev;    /* kSrcRing rows of 2*src_n doubles */
     double *src_host;   /* pinned mirror */
     cudaEvent_t ev_src; /* last upload of the ring finished */

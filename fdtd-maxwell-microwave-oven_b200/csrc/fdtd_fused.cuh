@@ -101,7 +101,7 @@ __device__ __forceinline__ void fused_sweep(const Geo &g, const Fld &a, const Fl
             for (int r = 0; r < TY; ++r)
                 eyl[r] = __ldg(pey + (q - 1 + r * P));
         }
-        if (s.on && kstart == 1) { /* first set_source: Ex = 0 on the patch (main.c:749) */
+        if (s.on && kstart == s.kl) { /* first set_source: Ex = 0 on the patch (main.c:749) */
 #pragma unroll
             for (int rr = 0; rr < NR; ++rr)
                 if (in_patch(s, i, jb - 1 + rr))
@@ -118,7 +118,7 @@ __device__ __forceinline__ void fused_sweep(const Geo &g, const Fld &a, const Fl
         hxm[r] = hym[r] = 0.0;
 
     for (int kl = kstart; kl < kl1; ++kl, pl += g.PR) {
-        const bool srck = s.on && kl == 1; /* global plane k = 0 carries the source */
+        const bool srck = s.on && kl == s.kl; /* global plane k = 0 carries the source */
         const double *pex = a.ex + pl, *pey = a.ey + pl, *pez = a.ez + pl;
         const double *phx = a.hx + pl, *phy = a.hy + pl, *phz = a.hz + pl;
 

@@ -164,7 +164,7 @@ __device__ __forceinline__ void fused_tma_sweep(const Geo &g, const TmaMaps &map
             for (int r = 0; r < TY; ++r)
                 eyl[r] = sey[c0 - 1 + (r + 1) * W];
         }
-        if (s.on && kstart == 1) {
+        if (s.on && kstart == s.kl) {
 #pragma unroll
             for (int rr = 0; rr < NR; ++rr)
                 if (in_patch(s, i, jb - 1 + rr))
@@ -188,7 +188,7 @@ __device__ __forceinline__ void fused_tma_sweep(const Geo &g, const TmaMaps &map
     int slot = 0;        /* ring slot of plane kl */
     unsigned phase = 0;  /* mbarrier phase parity of that slot's current fill */
     for (int kl = kstart, n = 0; kl < kl1; ++kl, ++n, pl += g.PR) {
-        const bool srck = s.on && kl == 1;
+        const bool srck = s.on && kl == s.kl;
         int slot1 = slot + 1;
         unsigned phase1 = phase;
         if (slot1 == stages) {

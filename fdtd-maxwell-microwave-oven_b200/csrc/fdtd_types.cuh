@@ -45,9 +45,12 @@ struct Fld {
 
 /* Waveguide source (main.c:712-753) in fused form.  vals[0..n) are the Ez amplitudes and
  * vals[n..2n) the Hx amplitudes of this step, computed on the host with glibc (fdtd_source_values).
- * on == 0 in validation mode and on slabs that do not hold the global plane k = 0. */
+ * on == 0 in validation mode and on slabs that never touch the global plane k = 0; kl = local index of
+ * that plane: 1 on the slab that owns it, 0 on a slab that starts at k = 1 (the fused step recomputes
+ * H of the plane below its slab, which then is the source plane). */
 struct Src {
     int on;
+    int kl;
     int i0, i1, j0, j1;
     int n;
     const double *vals;

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256, MarchCfg<TY>::kMinBlocks) k_update_h_marc
     }
 
     long long o = i + (long long)g.P * (jb + (long long)g.R * kl0);
-    const bool src_chunk = s.on && kl0 == 1; /* this chunk starts on the global plane k = 0 */
+    const bool src_chunk = s.on && kl0 == s.kl; /* this chunk starts on the global plane k = 0 */
 
     /* plane kl0 of Ex (TY+1 rows) and Ey (TY rows) */
     double exk[TY + 1], eyk[TY];
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256, MarchCfg<TY>::kMinBlocks) k_update_h_marc
 
     for (int kl = kl0; kl < kl1; ++kl, o += g.PR) {
         const bool cell = kl <= g.nk;           /* Hx, Hy, Ez exist on this plane */
-        const bool srck = s.on && kl == 1;      /* global plane k = 0 carries the source */
+        const bool srck = s.on && kl == s.kl;      /* global plane k = 0 carries the source */
 
         double exn[TY + 1], eyn[TY], ezk[TY + 1], hx[TY], hy[TY], hz[TY];
 #pragma unroll
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256, MarchCfg<TY>::kMinBlocks) k_update_e_marc
 
     for (int kl = kl0; kl < kl1; ++kl, o += g.PR) {
         const bool kin = (kl - 1 + g.kbase) >= 1; /* Ex, Ey are updated on this plane */
-        const bool srck = s.on && kl == 1;
+        const bool srck = s.on && kl == s.kl;
 
         double hxk[TY + 1], hzk[TY + 1], hyk[TY], ex[TY], ey[TY], ez[TY];
 #pragma unroll

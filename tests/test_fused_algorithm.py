@@ -103,7 +103,9 @@ def _worker(rank, world, port, dims, mode, steps, ret):
         t = 0.0
         for _ in range(steps):
             src = None
-            if plan is not None and k0 == 0:        # the source lives on the slab that holds k = 0
+            # the source lives on the slab that holds k = 0 -- and the slab that starts at k = 1 needs the
+            # amplitudes too: it recomputes H of plane k = 0 (the plane below it), source included
+            if plan is not None and k0 <= 1:
                 ez, hx = F.source_values(p, plan, t)
                 src = (plan.i0, plan.i1, plan.j0, plan.j1, ez, hx)
             fused_step(a, b, dims, ch, ce, src, kchunk=3, klo=k0, khi=k1)
@@ -125,7 +127,7 @@ def _worker(rank, world, port, dims, mode, steps, ret):
 
 
 @pytest.mark.parametrize("world,dims,mode,steps", [(2, (23, 19, 12), 1, 6), (3, (21, 17, 10), 1, 5),
-                                                    (2, (12, 14, 9), 0, 5)])
+                                                    (2, (12, 14, 9), 0, 5), (4, (12, 14, 4), 1, 5)])
 def test_fused_slabs_with_fused_halo_plan(world, dims, mode, steps):
     ctx = mp.get_context("spawn")
     ret = ctx.Manager().dict()
