@@ -5,13 +5,17 @@
  *
  *     ./microwave params.txt          (same 8-number file, main.c:216-242)
  *
- * Output.  The reference writes one Silo file per dump, r/result%04d.silo (main.c:19, :550-598).
- * libsilo is not available in this image, so the dump sink below writes the same variables --
- * same names, same order, same zone-centred doubles, x fastest -- as a raw brick plus one
- * VisIt "BOV" header per variable:  r/result%04d.raw  and  r/result%04d.<var>.bov .
- * The sink is a three-function table (fdtd_dump_sink); a Silo-backed sink is a drop-in where
- * libsilo exists.  As in the reference the directory r/ must already exist;
- * if it does not, the run fails with the reference's message "Could not create DB".
+ * Output.  Like the reference: one Silo file per dump, r/result%04d.silo (main.c:19, :550-598), in the
+ * PDB driver's format, holding the quadmesh "mesh" (collinear, coordinates i * dx, dims I+1, J+1, K+1),
+ * the zone-centred double quadvars "ex" .. "hz" (+ "aEy", "aHx", "aHz" in validation mode) and the
+ * defvars "vecs" (E = {ex, ey, ez}, H = {hx, hy, hz}).  libsilo is not available in this image, so the
+ * files are written by host/silo_pdb.c, a minimal writer of that format.  With FDTD_B200_GPUS=N every
+ * slab writes its block r/result%04d.slab<r>.silo and the root file r/result%04d.silo holds a
+ * multimesh "mesh" and multivars "ex" .. over the blocks (Silo's multi-block convention).
+ * FDTD_B200_SINK=raw selects the earlier output instead: a raw brick r/result%04d.raw plus one VisIt
+ * "BOV" header per variable.  The sink is a three-function table (fdtd_dump_sink); a libsilo-backed
+ * sink is a drop-in where libsilo exists.  As in the reference the directory r/ must
+ * already exist; if it does not, the run fails with the reference's message "Could not create DB".
  *
  * Environment: FDTD_B200_DEVICE (CUDA device index, default 0), FDTD_B200_GPUS=N (split the cavity
  * into N z-slabs on GPUs 0..N-1 of this box, or on the devices FDTD_B200_DEVICES=a,b,... names; still
@@ -21,6 +25,7 @@
  */
 #define _POSIX_C_SOURCE 199309L
 #include "fdtd_b200.h"
+#include "silo_pdb.h"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -112,6 +117,108 @@ static int sink_end(void *user)
     return 0;
 }
 
+/* ---- the Silo sink ---------------------------------------------------------------------------- */
+
+typedef struct silo_sink {
+    int slab, nslabs;
+    spdb_file *db;
+    int iteration;
+    size_t dims[3], k0;
+    double dx;
+    int nvars;
+    char names[16][8];
+} silo_sink;
+
+/* <-> DBCreate + DBPutQuadmesh, main.c:553-561 (coordinates as compute_oven() makes them, main.c:270-278) */
+static int silo_begin(void *user, int iteration, const size_t dims[3], size_t k0)
+{
+    silo_sink *s = (silo_sink *)user;
+    char name[160];
+    double *xyz[3];
+    const double *cxyz[3];
+    int mdims[3], d, rc;
+    size_t i;
+    if (s->nslabs > 1)
+        snprintf(name, sizeof name, "r/result%04d.slab%d.silo", iteration, s->slab);
+    else
+        snprintf(name, sizeof name, "r/result%04d.silo", iteration);
+    s->db = spdb_create(name, NULL);
+    if (!s->db)
+        return -1;
+    s->iteration = iteration;
+    memcpy(s->dims, dims, sizeof s->dims);
+    s->k0 = k0;
+    s->nvars = 0;
+    for (d = 0; d < 3; ++d) {
+        mdims[d] = (int)dims[d] + 1;
+        xyz[d] = (double *)malloc(sizeof(double) * (dims[d] + 1));
+        if (!xyz[d])
+            return -1;
+        for (i = 0; i < dims[d] + 1; ++i)
+            xyz[d][i] = (double)(int)(i + (d == 2 ? k0 : 0)) * s->dx;
+        cxyz[d] = xyz[d];
+    }
+    rc = spdb_put_quadmesh(s->db, "mesh", cxyz, mdims);
+    for (d = 0; d < 3; ++d)
+        free(xyz[d]);
+    return rc;
+}
+
+/* <-> DBPutQuadvar1, main.c:564-588 */
+static int silo_variable(void *user, const char *name, const double *data, size_t count)
+{
+    silo_sink *s = (silo_sink *)user;
+    const int zdims[3] = {(int)s->dims[0], (int)s->dims[1], (int)s->dims[2]};
+    if (s->nvars < 16)
+        snprintf(s->names[s->nvars++], sizeof s->names[0], "%s", name);
+    if (spdb_quadvar_begin(s->db, name, "mesh", zdims) != 0 || spdb_quadvar_append(s->db, data, count) != 0)
+        return -1;
+    return spdb_quadvar_end(s->db);
+}
+
+static int put_vecs(spdb_file *db)
+{
+    const char *names[] = {"E", "H"};
+    const char *defs[] = {"{ex, ey, ez}", "{hx, hy, hz}"};
+    const int types[] = {SPDB_VARTYPE_VECTOR, SPDB_VARTYPE_VECTOR};
+    return spdb_put_defvars(db, "vecs", 2, names, types, defs); /* main.c:591-595 */
+}
+
+/* <-> DBPutDefvars + DBClose, main.c:591-597; slab 0 of a multi-slab run also writes the root file */
+static int silo_end(void *user)
+{
+    silo_sink *s = (silo_sink *)user;
+    int rc = put_vecs(s->db);
+    if (spdb_close(s->db) != 0)
+        rc = -1;
+    s->db = NULL;
+    if (rc == 0 && s->nslabs > 1 && s->slab == 0) {
+        char name[160], blocks[64][96];
+        const char *ptrs[64];
+        spdb_file *root;
+        int r, v;
+        snprintf(name, sizeof name, "r/result%04d.silo", s->iteration);
+        root = spdb_create(name, NULL);
+        if (!root)
+            return -1;
+        for (r = 0; r < s->nslabs; ++r) {
+            snprintf(blocks[r], sizeof blocks[r], "result%04d.slab%d.silo:/mesh", s->iteration, r);
+            ptrs[r] = blocks[r];
+        }
+        rc = spdb_put_multimesh(root, "mesh", s->nslabs, ptrs);
+        for (v = 0; v < s->nvars && rc == 0; ++v) {
+            for (r = 0; r < s->nslabs; ++r)
+                snprintf(blocks[r], sizeof blocks[r], "result%04d.slab%d.silo:/%s", s->iteration, r, s->names[v]);
+            rc = spdb_put_multivar(root, s->names[v], s->nslabs, ptrs);
+        }
+        if (rc == 0)
+            rc = put_vecs(root);
+        if (spdb_close(root) != 0)
+            rc = -1;
+    }
+    return rc;
+}
+
 static double now_s(void)
 {
     struct timespec ts;
@@ -125,7 +232,10 @@ int main(int argc, const char *argv[])
     fdtd_ctx *ctx = NULL;
     fdtd_group *group = NULL;
     static file_sink files[64];
+    static silo_sink silos[64];
     fdtd_dump_sink sinks[64];
+    const char *sink_env = getenv("FDTD_B200_SINK");
+    const int raw_sink = sink_env && !strcmp(sink_env, "raw");
     size_t steps = 0;
     double t_end = 0.0, t0, t1;
     const char *dev_env = getenv("FDTD_B200_DEVICE");
@@ -186,14 +296,18 @@ int main(int argc, const char *argv[])
     printf("Launching simulation\n");
     fflush(stdout);
     memset(files, 0, sizeof files);
+    memset(silos, 0, sizeof silos);
     for (r = 0; r < ngpus; ++r) {
         files[r].slab = r;
         files[r].nslabs = ngpus;
         files[r].dx = params.spatial_step;
-        sinks[r].user = &files[r];
-        sinks[r].begin = sink_begin;
-        sinks[r].variable = sink_variable;
-        sinks[r].end = sink_end;
+        silos[r].slab = r;
+        silos[r].nslabs = ngpus;
+        silos[r].dx = params.spatial_step;
+        sinks[r].user = raw_sink ? (void *)&files[r] : (void *)&silos[r];
+        sinks[r].begin = raw_sink ? sink_begin : silo_begin;
+        sinks[r].variable = raw_sink ? sink_variable : silo_variable;
+        sinks[r].end = raw_sink ? sink_end : silo_end;
     }
     t0 = now_s();
     if (group)

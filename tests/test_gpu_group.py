@@ -9,6 +9,7 @@ import pytest
 import torch
 
 from conftest import ROOT, bits_equal, to_oracle_params, upper
+from pdb_reader import SiloFile
 
 pytestmark = pytest.mark.gpu
 EXE = os.path.join(ROOT, "fdtd-maxwell-microwave-oven_b200", "microwave")
@@ -170,3 +171,32 @@ def test_many_short_runs_back_to_back_on_thin_slabs(F, oracle, kernel):
             got = g.download()
         for k, want in f.items():
             assert bits_equal(got[k[0].upper() + k[1:]], want), (world, transport, k)
+
+
+def test_microwave_two_slabs_write_silo_multiblock(F, golden, tmp_path):
+    """FDTD_B200_GPUS=2 with the default sink: one block file per slab and a root file with multimesh /
+    multivar objects naming the blocks; the blocks' data add up to the reference's dump."""
+    g_ = golden["propagate_tiny"]["mode0"]
+    (tmp_path / "params.txt").write_text("\n".join(g_["params"]))
+    (tmp_path / "r").mkdir()
+    r = subprocess.run([EXE, "params.txt"], cwd=tmp_path, capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, FDTD_B200_GPUS="2", FDTD_B200_DEVICES=f"0,{1 % ngpu()}"))
+    assert r.returncode == 0, r.stderr
+    nx, ny, nz = g_["grid"]
+    dx = float(g_["params"][3])
+    names = ["ex", "ey", "ez", "hx", "hy", "hz", "aEy", "aHx", "aHz"]
+    for d in g_["dumps"]:
+        root = SiloFile(tmp_path / d["file"])
+        base = os.path.basename(d["file"]).replace(".silo", "")
+        mm = root.object("mesh")
+        assert mm["_type"] == "multimesh" and mm["nblocks"] == 2
+        assert mm["meshnames"] == f";{base}.slab0.silo:/mesh;{base}.slab1.silo:/mesh"
+        assert root.objects() == ["mesh"] + names + ["vecs"]
+        blocks = [SiloFile(tmp_path / "r" / f"{base}.slab{rr}.silo") for rr in range(2)]
+        z = np.concatenate([b.object("mesh")["coord2"] for b in blocks])
+        k = [F.slab_range(nz, rr, 2) for rr in range(2)]
+        assert np.array_equal(z, np.concatenate([np.arange(a, b + 1) * dx for a, b in k]))
+        for name in names:
+            assert root.object(name)["_type"] == "multivar"
+            whole = np.concatenate([b.object(name)["value0"] for b in blocks])
+            assert digest(whole) == d["vars"][name], (base, name)

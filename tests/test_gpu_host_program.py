@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 from conftest import ROOT
+from pdb_reader import SiloFile
 
 pytestmark = pytest.mark.gpu
 EXE = os.path.join(ROOT, "fdtd-maxwell-microwave-oven_b200", "microwave")
@@ -32,7 +33,10 @@ def exe(F):
 
 
 @pytest.mark.parametrize("mode", [0, 1])
-def test_microwave_reproduces_reference_run(exe, golden, tmp_path, mode):
+def test_microwave_writes_the_reference_silo_files(exe, golden, tmp_path, mode):
+    """./microwave params.txt writes r/result%04d.silo (PDB driver layout) with the mesh, the variables and
+    the defvars of write_silo(), main.c:550-598; parsed back with the independent reader, every variable
+    has the sha256 of the reference's own dump."""
     g = golden["propagate_tiny"][f"mode{mode}"]
     (tmp_path / "params.txt").write_text("\n".join(g["params"]))
     (tmp_path / "r").mkdir()
@@ -40,6 +44,36 @@ def test_microwave_reproduces_reference_run(exe, golden, tmp_path, mode):
     assert r.returncode == 0, r.stderr
     want = STDOUT_HEAD + (["Validation mode activated. "] if mode == 0 else []) + STDOUT_TAIL
     assert r.stdout.splitlines() == want
+    nx, ny, nz = g["grid"]
+    names = ["ex", "ey", "ez", "hx", "hy", "hz"] + (["aEy", "aHx", "aHz"] if mode == 0 else [])
+    files = sorted(p.name for p in (tmp_path / "r").iterdir())
+    assert files == [os.path.basename(d["file"]) for d in g["dumps"]]       # result0001.silo, ... and nothing else
+    dx = float(g["params"][3])
+    for d in g["dumps"]:
+        s = SiloFile(tmp_path / d["file"])
+        assert s.objects() == ["mesh"] + names + ["vecs"]
+        mesh = s.object("mesh")
+        assert mesh["_type"] == "quadmesh" and list(mesh["dims"]) == [nx + 1, ny + 1, nz + 1]   # main.c:257-259
+        for axis, n in enumerate((nx, ny, nz)):
+            assert np.array_equal(mesh[f"coord{axis}"], np.arange(n + 1) * dx)                  # main.c:270-278
+        for name in names:
+            v = s.object(name)
+            assert v["_type"] == "quadvar" and v["meshid"] == "mesh" and list(v["dims"]) == [nx, ny, nz]
+            assert v["centering"] == 111 and v["datatype"] == 20                                # DB_ZONECENT, DB_DOUBLE
+            assert digest(v["value0"]) == d["vars"][name], (d["file"], name)
+        vecs = s.object("vecs")
+        assert vecs["names"] == ";E;H" and vecs["defns"] == ";{ex, ey, ez};{hx, hy, hz}"          # main.c:591-593
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_microwave_raw_sink(exe, golden, tmp_path, mode):
+    """FDTD_B200_SINK=raw: the same variables as one raw brick plus a VisIt BOV header per variable"""
+    g = golden["propagate_tiny"][f"mode{mode}"]
+    (tmp_path / "params.txt").write_text("\n".join(g["params"]))
+    (tmp_path / "r").mkdir()
+    r = subprocess.run([exe, "params.txt"], cwd=tmp_path, capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, FDTD_B200_SINK="raw"))
+    assert r.returncode == 0, r.stderr
     nx, ny, nz = g["grid"]
     n = nx * ny * nz
     names = ["ex", "ey", "ez", "hx", "hy", "hz"] + (["aEy", "aHx", "aHz"] if mode == 0 else [])
