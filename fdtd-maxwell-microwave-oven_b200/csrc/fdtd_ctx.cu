@@ -12,6 +12,7 @@
 #include "fdtd_update.cuh"
 #include "fdtd_fused.cuh"
 #include "fdtd_fused_tma.cuh"
+#include "fdtd_step2_tma.cuh"
 
 using namespace fdtdi;
 
@@ -23,7 +24,7 @@ int check_ctx(const fdtd_ctx *c, const char *who)
         fdtd_set_error("%s: context is NULL", who);
         return FDTD_E_ARG;
     }
-    if (c->opt_wx * c->opt_wy > (c->opt_kernel == 3 ? 16 : 8)) { /* a block is at most 256 threads (512 for the TMA kernel) */
+    if (c->opt_kernel != 4 && c->opt_wx * c->opt_wy > (c->opt_kernel == 3 ? 16 : 8)) { /* a block is at most 256 threads (512 for the TMA kernel) */
         fdtd_set_error("%s: options warps_x (%ld) * warps_y (%ld) must be <= %d for kernel %ld", who, c->opt_wx, c->opt_wy,
                        c->opt_kernel == 3 ? 16 : 8, c->opt_kernel);
         return FDTD_E_ARG;
@@ -344,6 +345,13 @@ int launch_fused_tma_t(fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cuda
  * the generic instantiation */
 int launch_fused_tma(fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStream_t st)
 {
+    if (c->opt_kernel == 4) { /* a single step on a context that otherwise takes two per sweep: the default shape */
+        const long keep_wx = c->opt_wx, keep_wy = c->opt_wy, keep_st = c->opt_stages, keep_kc = c->opt_kchunk;
+        c->opt_wx = 1; c->opt_wy = 8; c->opt_stages = 4; c->opt_kchunk = 32;
+        const int rc = launch_fused_tma_t<1, 1, 8>(c, s, kl_begin, kl_end, st);
+        c->opt_wx = keep_wx; c->opt_wy = keep_wy; c->opt_stages = keep_st; c->opt_kchunk = keep_kc;
+        return rc;
+    }
     const long ty = c->opt_strip == 1 ? 1 : 2, wx = c->opt_wx, wy = c->opt_wy;
     if (ty == 2 && wx == 4 && wy == 2) return launch_fused_tma_t<2, 4, 2>(c, s, kl_begin, kl_end, st);
     if (ty == 2 && wx == 2 && wy == 2) return launch_fused_tma_t<2, 2, 2>(c, s, kl_begin, kl_end, st);
@@ -364,7 +372,7 @@ void launch_fused(fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStrea
 {
     if (kl_end <= kl_begin)
         return;
-    if (c->opt_kernel == 3) {
+    if (c->opt_kernel >= 3) {
         const int rc = launch_fused_tma(c, s, kl_begin, kl_end, st);
         if (rc != FDTD_OK)
             c->launch_error = rc;
@@ -376,6 +384,49 @@ void launch_fused(fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStrea
     case 4: launch_fused_t<4>(c, s, kl_begin, kl_end, st); break;
     default: launch_fused_t<2>(c, s, kl_begin, kl_end, st); break;
     }
+}
+
+/* two whole steps of the local planes [kl_begin, kl_end) in one sweep: reads c->f, writes c->f2 */
+template <int WY>
+int launch_step2_t(fdtd_ctx *c, const Src &s1, const Src &s2, int kl_begin, int kl_end, cudaStream_t st)
+{
+    constexpr int BYE = 2 * WY;
+    FDTD_TRY(encode_maps(c, kS2BoxW - 4, BYE - 1));
+    /* as many stages as asked for, as far as the shared memory of one SM goes (at least two) */
+    const size_t stage_bytes = (size_t)6 * tma_box_doubles(kS2BoxW - 4, BYE - 1) * sizeof(double);
+    const int stages = (int)std::max(2L, std::min(c->opt_stages, (long)(200 * 1024 / stage_bytes)));
+    const size_t smem = (size_t)stages * stage_bytes;
+    const void *fn = (const void *)k_step2_tma<WY>;
+    bool configured = false;
+    for (int k = 0; k < c->n_smem_optin; ++k)
+        configured = configured || c->smem_optin[k] == fn;
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(k_step2_tma<WY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if (c->n_smem_optin < 16)
+            c->smem_optin[c->n_smem_optin++] = fn;
+    }
+    Span sp{kl_begin, kl_end, (int)std::max(c->opt_kchunk, 4L), 0};
+    dim3 block(32, WY);
+    dim3 grid((c->g.I + 1 + kS2TileX - 1) / kS2TileX, (c->g.J + 1 + BYE - 4) / (BYE - 3),
+              (kl_end - kl_begin + sp.kchunk - 1) / sp.kchunk);
+    Src2 src{s1, s2};
+    k_step2_tma<WY><<<grid, block, smem, st>>>(c->g, c->tma_maps[0], c->f2, c->ch, c->ce, src, sp, stages);
+    ++c->launches;
+    return FDTD_OK;
+}
+
+int launch_step2(fdtd_ctx *c, const Src &s1, const Src &s2, int kl_begin, int kl_end, cudaStream_t st)
+{
+    if (kl_end <= kl_begin)
+        return FDTD_OK;
+    int rc;
+    if (c->opt_wy >= 16)
+        rc = launch_step2_t<16>(c, s1, s2, kl_begin, kl_end, st);
+    else if (c->opt_wy >= 12)
+        rc = launch_step2_t<12>(c, s1, s2, kl_begin, kl_end, st);
+    else
+        rc = launch_step2_t<8>(c, s1, s2, kl_begin, kl_end, st);
+    return rc;
 }
 
 void launch_set_source(const fdtd_ctx *c, const double *row_dev, cudaStream_t st)
@@ -606,7 +657,27 @@ int run_impl(fdtd_ctx *c, size_t steps, double *time_counter, float *total_ms, f
         for (size_t s = 0; s < chunk; ++s) {
             const Src src = make_src(c, c->src_dev + s * row);
             const size_t gs = done + s;
-            if (per_kernel && gs * 3 + 2 < evs.size())
+            const bool ev = per_kernel && gs * 3 + 2 < evs.size();
+            if (c->opt_kernel == 4 && s + 1 < chunk) {
+                /* two steps in one sweep: reads c->f, writes c->f2, then the two swap */
+                const Src src2 = make_src(c, c->src_dev + (s + 1) * row);
+                const bool ev2 = per_kernel && (gs + 1) * 3 + 2 < evs.size();
+                if (ev)
+                    CUDA_TRY(cudaEventRecord(evs[3 * gs], c->s_main));
+                FDTD_TRY(launch_step2(c, src, src2, 1, c->g.nk + c->g.top + 1, c->s_main));
+                swap_buffers(c);
+                CUDA_TRY(cudaGetLastError());
+                if (ev) { /* the sweep is booked on the first of its two steps */
+                    CUDA_TRY(cudaEventRecord(evs[3 * gs + 1], c->s_main));
+                    CUDA_TRY(cudaEventRecord(evs[3 * gs + 2], c->s_main));
+                }
+                if (ev2)
+                    for (int e = 0; e < 3; ++e)
+                        CUDA_TRY(cudaEventRecord(evs[3 * (gs + 1) + e], c->s_main));
+                ++s;
+                continue;
+            }
+            if (ev)
                 FDTD_TRY(queue_step(c, src, evs[3 * gs], evs[3 * gs + 1], evs[3 * gs + 2]));
             else
                 FDTD_TRY(queue_step(c, src, nullptr, nullptr, nullptr));
@@ -843,7 +914,16 @@ int fdtd_ctx_set_option(fdtd_ctx *c, const char *key, long value)
         fdtd_set_error("fdtd_ctx_set_option: NULL key");
         return FDTD_E_ARG;
     }
-    if (!strcmp(key, "kernel") && value >= 0 && value <= 3) {
+    if (!strcmp(key, "kernel") && value >= 0 && value <= 4) {
+        if (value == 4 && c->nranks > 1) {
+            fdtd_set_error("fdtd_ctx_set_option: kernel 4 (two steps per sweep) runs on single-slab contexts only");
+            return FDTD_E_ARG;
+        }
+        if (value == 4 && c->opt_kernel != 4) { /* its own launch defaults */
+            c->opt_wy = 8;
+            c->opt_stages = 3;
+            c->opt_kchunk = 64;
+        }
         c->opt_kernel = value;
         c->kernel_auto = false;
     }
@@ -851,7 +931,7 @@ int fdtd_ctx_set_option(fdtd_ctx *c, const char *key, long value)
     else if (!strcmp(key, "strip") && value >= 1 && value <= 4) c->opt_strip = value;
     else if (!strcmp(key, "kchunk") && value >= 1 && value <= 1 << 20) c->opt_kchunk = value;
     else if (!strcmp(key, "warps_x") && value >= 1 && value <= 8) c->opt_wx = value;
-    else if (!strcmp(key, "warps_y") && value >= 1 && value <= 8) c->opt_wy = value;
+    else if (!strcmp(key, "warps_y") && value >= 1 && value <= (c->opt_kernel == 4 ? 16 : 8)) c->opt_wy = value;
     else if (!strcmp(key, "prefetch") && value >= 0 && value <= 64) c->opt_prefetch = value;
     else if (!strcmp(key, "host_chunk") && value >= 0 && value <= 1 << 20) c->opt_host_chunk = value;
     else if (!strcmp(key, "host_pipeline") && value >= 0 && value <= 1) c->opt_host_pipeline = value;

@@ -1,0 +1,342 @@
+/*
+ * fdtd_step2_tma.cuh -- TWO time steps per sweep ("kernel" = 4): temporal blocking on top of the
+ * TMA-staged fused sweep of fdtd_fused_tma.cuh.
+ *
+ * Why.  k_step_fused_tma moves every array once in and once out per time step (96 B per cell-update)
+ * and runs at 0.9 of the HBM copy rate (profiles/r02_tma_default_*): only fewer bytes can make it
+ * faster.  Here one sweep advances the state by two steps, so the six arrays are read and written
+ * once per TWO steps: 48 B per cell-update plus the overlap of the tiles.
+ *
+ * How.  Sweeping planes upward, iteration k brings in plane k+1 of the old state (time n) and does
+ *     A   H1(k)   = H0(k)   + cH * curl E0(k, k+1)          time n + 1/2
+ *     B   E1(k)   = E0(k)   + cE * curl H1(k, k-1)          time n + 1
+ *     C   H2(k-1) = H1(k-1) + cH * curl E1(k-1, k)          time n + 3/2
+ *     D   E2(k-1) = E1(k-1) + cE * curl H2(k-1, k-2)        time n + 2   -> stored with H2(k-1)
+ * Every thread owns one column (i) and two rows (j, j+1) of an EXTENDED tile of 32 x 2*WY sites and
+ * evaluates all four stages there; what a stage needs from the neighbouring sites comes from the
+ * neighbouring lanes (shuffles, x) or, across warps, from one row per warp in shared memory (y).
+ * Nothing is recomputed and nothing is special at tile edges: the outermost sites of the extended
+ * tile simply compute values nobody uses.  Each stage loses one ring of validity, so the tile that is
+ * stored is 28 x (2*WY - 3): tiles overlap by 4 columns and 3 rows (71 % useful sites for WY = 8) --
+ * the price of halving the HBM traffic.  The 28-column pitch keeps every box start even (TMA needs
+ * 16-byte aligned boxes) and every stored row sector-aligned.
+ *
+ * A chunk of planes [a, b) starts two planes early (H1(a-2), then H1/E1(a-1), then H2(a-1)) and reads
+ * up to plane b+1; with 32..64 planes per chunk that is 6..12 % extra reads.
+ *
+ * The arithmetic per element is the reference's (yee() in fdtd_types.cuh, operand order of
+ * main.c:448-461, 486-499, no FMA), PEC walls are elements whose update is skipped at BOTH levels,
+ * and the source of main.c:712-753 is substituted at both levels with the amplitudes of its own time
+ * (SURVEY.md B.4): results stay bit-identical to two passes of the sequential loop body.
+ */
+#pragma once
+
+#include "fdtd_fused_tma.cuh"
+
+namespace fdtd {
+
+constexpr int kS2TileX = 28;      /* stored columns per block */
+constexpr int kS2BoxW = 34;       /* loaded columns: 32 sites + the +1 neighbour, padded to an even width */
+
+struct Src2 {
+    Src s1, s2; /* amplitudes of the first and of the second step */
+};
+
+template <int WY, bool EDGE>
+__device__ __forceinline__ void step2_sweep(const Geo &g, const TmaMaps &maps, const Fld &b, const double cH,
+                                            const double cE, const Src2 &src, const int stages, double *ring,
+                                            double *xh, double *xe, unsigned long long *full, const int X0,
+                                            const int Y0, const int kl0, const int kl1)
+{
+    constexpr int BYE = 2 * WY, W = kS2BoxW, HH = BYE + 1;
+    const int box = tma_box_doubles(W - 4, HH - 2);
+    const int stage_doubles = 6 * box;
+    const int lane = threadIdx.x, w = threadIdx.y;
+    const int i = X0 - 2 + lane;
+    const int j0 = Y0 - 2 + 2 * w;
+    const int P = g.P;
+    const bool leader = lane == 0 && w == 0;
+    const Src &s1 = src.s1, &s2 = src.s2;
+
+    /* what this thread may update / store (EDGE blocks only; interior blocks have everything true
+     * except the output window) */
+    bool up_x[2], up_y[2], up_z[2], st_nc[2], st_cn[2], st_cc[2], st_nn[2];
+    const bool outx = lane >= 2 && lane < 30;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int j = j0 + r, row = 2 * w + r;
+        const bool out = outx && row >= 2 && row < BYE - 1;
+        if (EDGE) {
+            const bool xn = i >= 0 && i <= g.I, xc = i >= 0 && i < g.I, xi = i >= 1 && i < g.I;
+            const bool jn = j >= 0 && j <= g.J, jc = j >= 0 && j < g.J, ji = j >= 1 && j < g.J;
+            up_x[r] = xc && ji;
+            up_y[r] = xi && jc;
+            up_z[r] = xi && ji;
+            st_nc[r] = out && xn && jc;
+            st_cn[r] = out && xc && jn;
+            st_cc[r] = out && xc && jc;
+            st_nn[r] = out && xn && jn;
+        } else {
+            up_x[r] = up_y[r] = up_z[r] = true;
+            st_nc[r] = st_cn[r] = st_cc[r] = st_nn[r] = out;
+        }
+    }
+
+    const int g0 = 1 - g.kbase;                /* local index of the global plane k = 0 */
+    const int kstart = max(kl0 - 2, g0);
+    const int nplanes = kl1 - kstart + 2;      /* planes kstart .. kl1 + 1 are loaded */
+    const unsigned full_bytes = 6u * (unsigned)(W * HH) * 8u;
+
+    auto issue = [&](int slot, int n) {
+        double *dst = ring + (size_t)slot * stage_doubles;
+        unsigned long long *bar = full + slot;
+        const int plane = kstart + n;
+        tma::mbar_expect_tx(bar, full_bytes);
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+            tma::load_box(dst + a * box, &maps.m[a], X0 - 2, Y0 - 2, plane, bar);
+    };
+    if (leader)
+        for (int n = 0; n < stages && n < nplanes; ++n)
+            issue(n, n);
+
+    const int c0 = lane + W * (2 * w);         /* (i, j0) inside a box */
+    const int xrow = w * 32 + lane;            /* this thread's slot in an exchange row */
+    const int xrow_dn = max(w - 1, 0) * 32 + lane, xrow_up = min(w + 1, WY - 1) * 32 + lane;
+    double *xh_hx = xh, *xh_hz = xh + 32 * WY;                   /* top row of each strip: Hx, Hz */
+    double *xe_ex = xe, *xe_ez = xe + 2 * 32 * WY;               /* bottom row: Ex, Ez; two planes deep */
+
+    /* E0 of plane kstart (own sites) */
+    double ex0[2], ey0[2];
+    tma::mbar_wait(full + 0, 0);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        ex0[r] = ring[c0 + r * W];
+        ey0[r] = ring[box + c0 + r * W];
+    }
+    double hx1p[2] = {0, 0}, hy1p[2] = {0, 0}, hz1p[2] = {0, 0};      /* H1(k-1) */
+    double ex1p[2] = {0, 0}, ey1p[2] = {0, 0}, ez1p[2] = {0, 0};      /* E1(k-1) */
+    double hx2pp[2] = {0, 0}, hy2pp[2] = {0, 0};                      /* H2(k-2) */
+
+    long long pl = (long long)(kstart - 1) * g.PR;                     /* plane k-1, where stage D stores */
+    int slot = 0;
+    unsigned phase = 0;
+    for (int k = kstart, n = 0; k <= kl1; ++k, ++n, pl += g.PR) {
+        int slot1 = slot + 1;
+        unsigned phase1 = phase;
+        if (slot1 == stages) {
+            slot1 = 0;
+            phase1 ^= 1u;
+        }
+        const int slot_now = slot;
+        slot = slot1;
+        phase = phase1;
+        tma::mbar_wait(full + slot1, phase1);
+        const double *cur = ring + (size_t)slot_now * stage_doubles, *nxt = ring + (size_t)slot1 * stage_doubles;
+        const double *sex = cur, *sey = cur + box, *sez = cur + 2 * box;
+        const double *shx = cur + 3 * box, *shy = cur + 4 * box, *shz = cur + 5 * box;
+        const int gk = k - 1 + g.kbase;                     /* global index of plane k */
+        const bool cell1 = k <= g.nk, kin1 = gk >= 1 && cell1;
+        const bool cell2 = k - 1 <= g.nk, kin2 = gk - 1 >= 1 && cell2;
+        const bool srck1 = s1.on && k == s1.kl;             /* stage A/B work on the source plane */
+        const bool srck2 = s2.on && k - 1 == s2.kl;         /* stage C/D do */
+
+        /* ---- A: H1(k) ---- */
+        double ez0[2], ez0i[2], ez0j[2], ex0j[2], ey0i[2], ex0n[2], ey0n[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            ez0[r] = sez[c0 + r * W];
+            ez0i[r] = sez[c0 + 1 + r * W];
+            ey0i[r] = sey[c0 + 1 + r * W];
+            ex0n[r] = nxt[c0 + r * W];
+            ey0n[r] = nxt[box + c0 + r * W];
+        }
+        ez0j[0] = ez0[1];
+        ez0j[1] = sez[c0 + 2 * W];
+        ex0j[0] = ex0[1];
+        ex0j[1] = sex[c0 + 2 * W];
+        if (srck1) { /* first set_source of step 1: Ez = amplitude, Ex = 0 on the patch (main.c:748-749) */
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int j = j0 + r;
+                if (in_patch(s1, i, j)) {
+                    ez0[r] = s1.vals[i - s1.i0];
+                    ex0[r] = 0.0;
+                }
+                if (in_patch(s1, i + 1, j))
+                    ez0i[r] = s1.vals[i + 1 - s1.i0];
+                if (in_patch(s1, i, j + 1)) {
+                    ez0j[r] = s1.vals[i - s1.i0];
+                    ex0j[r] = 0.0;
+                }
+            }
+        }
+        double hx1[2], hy1[2], hz1[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            hx1[r] = yee(shx[c0 + r * W], cH, ey0n[r], ey0[r], ez0j[r], ez0[r]);
+            hy1[r] = yee(shy[c0 + r * W], cH, ez0i[r], ez0[r], ex0n[r], ex0[r]);
+            hz1[r] = yee(shz[c0 + r * W], cH, ex0j[r], ex0[r], ey0i[r], ey0[r]);
+        }
+        if (srck1) { /* second set_source of step 1 (main.c:750-751) */
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+                if (in_patch(s1, i, j0 + r)) {
+                    hx1[r] = s1.vals[s1.n + i - s1.i0];
+                    hz1[r] = 0.0;
+                }
+        }
+        xh_hx[xrow] = hx1[1];
+        xh_hz[xrow] = hz1[1];
+        __syncthreads(); /* 1: H1 rows visible; every thread is done with the stage of plane k */
+        if (leader && n + stages < nplanes)
+            issue(slot_now, n + stages);
+
+        /* ---- B: E1(k) ---- */
+        double ex1[2], ey1[2], ez1[2];
+        {
+            const double hxjm[2] = {xh_hx[xrow_dn], hx1[0]}, hzjm[2] = {xh_hz[xrow_dn], hz1[0]};
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const double hzim = __shfl_up_sync(0xffffffffu, hz1[r], 1);
+                const double hyim = __shfl_up_sync(0xffffffffu, hy1[r], 1);
+                ex1[r] = ex0[r];
+                ey1[r] = ey0[r];
+                ez1[r] = ez0[r];
+                if (kin1) {
+                    const double ux = yee(ex0[r], cE, hz1[r], hzjm[r], hy1[r], hy1p[r]);
+                    const double uy = yee(ey0[r], cE, hx1[r], hx1p[r], hz1[r], hzim);
+                    ex1[r] = up_x[r] ? ux : ex0[r];
+                    ey1[r] = up_y[r] ? uy : ey0[r];
+                }
+                if (cell1) {
+                    const double uz = yee(ez0[r], cE, hy1[r], hyim, hx1[r], hxjm[r]);
+                    ez1[r] = up_z[r] ? uz : ez0[r];
+                }
+            }
+        }
+        if (s2.on && k == s2.kl) { /* first set_source of step 2 overwrites the patch before anything reads it */
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+                if (in_patch(s2, i, j0 + r)) {
+                    ez1[r] = s2.vals[i - s2.i0];
+                    ex1[r] = 0.0;
+                }
+        }
+        double *xe_ex_k = xe_ex + (k & 1) * 32 * WY, *xe_ez_k = xe_ez + (k & 1) * 32 * WY;
+        const double *xe_ex_p = xe_ex + ((k & 1) ^ 1) * 32 * WY, *xe_ez_p = xe_ez + ((k & 1) ^ 1) * 32 * WY;
+        xe_ex_k[xrow] = ex1[0];
+        xe_ez_k[xrow] = ez1[0];
+        __syncthreads(); /* 2: (orders the H1 reads above before the H2 rows below) */
+
+        /* ---- C: H2(k-1) ---- */
+        double hx2[2], hy2[2], hz2[2];
+        {
+            const double ezjp[2] = {ez1p[1], xe_ez_p[xrow_up]}, exjp[2] = {ex1p[1], xe_ex_p[xrow_up]};
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const double ezip = __shfl_down_sync(0xffffffffu, ez1p[r], 1);
+                const double eyip = __shfl_down_sync(0xffffffffu, ey1p[r], 1);
+                hx2[r] = yee(hx1p[r], cH, ey1[r], ey1p[r], ezjp[r], ez1p[r]);
+                hy2[r] = yee(hy1p[r], cH, ezip, ez1p[r], ex1[r], ex1p[r]);
+                hz2[r] = yee(hz1p[r], cH, exjp[r], ex1p[r], eyip, ey1p[r]);
+            }
+        }
+        if (srck2) { /* second set_source of step 2 */
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+                if (in_patch(s2, i, j0 + r)) {
+                    hx2[r] = s2.vals[s2.n + i - s2.i0];
+                    hz2[r] = 0.0;
+                }
+        }
+        xh_hx[xrow] = hx2[1];
+        xh_hz[xrow] = hz2[1];
+        __syncthreads(); /* 3 */
+
+        /* ---- D: E2(k-1), stores ---- */
+        {
+            const double hxjm[2] = {xh_hx[xrow_dn], hx2[0]}, hzjm[2] = {xh_hz[xrow_dn], hz2[0]};
+            const bool store = k - 1 >= kl0;
+            double *qex = b.ex + pl, *qey = b.ey + pl, *qez = b.ez + pl;
+            double *qhx = b.hx + pl, *qhy = b.hy + pl, *qhz = b.hz + pl;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const double hzim = __shfl_up_sync(0xffffffffu, hz2[r], 1);
+                const double hyim = __shfl_up_sync(0xffffffffu, hy2[r], 1);
+                double vex = ex1p[r], vey = ey1p[r], vez = ez1p[r];
+                if (kin2) {
+                    const double ux = yee(vex, cE, hz2[r], hzjm[r], hy2[r], hy2pp[r]);
+                    const double uy = yee(vey, cE, hx2[r], hx2pp[r], hz2[r], hzim);
+                    vex = up_x[r] ? ux : vex;
+                    vey = up_y[r] ? uy : vey;
+                }
+                if (cell2) {
+                    const double uz = yee(vez, cE, hy2[r], hyim, hx2[r], hxjm[r]);
+                    vez = up_z[r] ? uz : vez;
+                }
+                if (store) {
+                    const int o = i + P * (j0 + r);
+                    if (cell2) {
+                        if (st_nc[r]) qhx[o] = hx2[r];
+                        if (st_cn[r]) qhy[o] = hy2[r];
+                        if (st_nn[r]) qez[o] = vez;
+                    }
+                    if (st_cc[r]) qhz[o] = hz2[r];
+                    if (st_cn[r]) qex[o] = vex;
+                    if (st_nc[r]) qey[o] = vey;
+                }
+            }
+        }
+
+        /* rotate */
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            hx2pp[r] = hx2[r];
+            hy2pp[r] = hy2[r];
+            hx1p[r] = hx1[r];
+            hy1p[r] = hy1[r];
+            hz1p[r] = hz1[r];
+            ex1p[r] = ex1[r];
+            ey1p[r] = ey1[r];
+            ez1p[r] = ez1[r];
+            ex0[r] = ex0n[r];
+            ey0[r] = ey0n[r];
+        }
+    }
+}
+
+/* block = 32 x WY threads, two resident blocks per SM */
+template <int WY>
+__global__ void __launch_bounds__(32 * WY, (WY > 8) ? 1 : 2)
+k_step2_tma(Geo g, const __grid_constant__ TmaMaps maps, Fld b, double cH, double cE, Src2 src, Span sp, int stages)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long full[kTmaMaxStages];
+    __shared__ double xh[2 * 32 * WY];
+    __shared__ double xe[4 * 32 * WY];
+    double *ring = reinterpret_cast<double *>(smem_raw);
+
+    constexpr int BYE = 2 * WY;
+    const int X0 = blockIdx.x * kS2TileX;
+    const int Y0 = blockIdx.y * (BYE - 3);
+    const int kl0 = sp.kl_begin + blockIdx.z * sp.kchunk;
+    const int kl1 = min(kl0 + sp.kchunk, sp.kl_end);
+
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        for (int st = 0; st < stages; ++st)
+            tma::mbar_init(full + st, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    /* every site of the extended tile strictly inside the walls: no predicate can be false */
+    const bool interior = X0 - 2 >= 1 && X0 + 29 < g.I && Y0 - 2 >= 1 && Y0 - 2 + BYE - 1 < g.J;
+    if (interior)
+        step2_sweep<WY, false>(g, maps, b, cH, cE, src, stages, ring, xh, xe, full, X0, Y0, kl0, kl1);
+    else
+        step2_sweep<WY, true>(g, maps, b, cH, cE, src, stages, ring, xh, xe, full, X0, Y0, kl0, kl1);
+}
+
+} /* namespace fdtd */

@@ -45,7 +45,12 @@ VARIANTS = [dict(kernel=0),
             dict(kernel=3, strip=1, kchunk=32, warps_x=1, warps_y=4, stages=3),
             dict(kernel=3, strip=2, kchunk=5, warps_x=2, warps_y=2, stages=2),
             dict(kernel=3, strip=2, kchunk=1000, warps_x=1, warps_y=8, stages=4),
-            dict(kernel=3, strip=1, kchunk=2, warps_x=2, warps_y=4, stages=8)]
+            dict(kernel=3, strip=1, kchunk=2, warps_x=2, warps_y=4, stages=8),
+            # two time steps per sweep (odd step counts finish with one single-step sweep)
+            dict(kernel=4),
+            dict(kernel=4, kchunk=4, warps_y=8, stages=2),
+            dict(kernel=4, kchunk=5, warps_y=16, stages=3),
+            dict(kernel=4, kchunk=1000, warps_y=12, stages=4)]
 GRIDS = [(0.037, 0.029, 0.023), (0.013, 0.011, 0.009), (0.05, 0.04, 0.03), (0.065, 0.033, 0.012),
          (0.034, 0.066, 0.007),
          # I a multiple of the tile width: the last block in x holds the single column i = I
@@ -141,7 +146,7 @@ def test_source_patch_must_fit(F):
 @pytest.mark.parametrize("name", ["stock_validation", "stock_computation", "ragged_50x39x29_computation",
                                   "random_37x28x23_computation", "random_33x17x9_validation",
                                   "cube128_computation_200"])
-@pytest.mark.parametrize("kernel", [1, 2, 3])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4])
 def test_golden_runs(F, golden, tmp_path, name, kernel):
     """Whole runs against digests of the reference's own output (tests/golden/digests.json)."""
     g = golden[name]
@@ -181,7 +186,7 @@ def test_golden_arrays_small_case(F, golden):
         assert_fields_equal(ctx.download(), {k: want[k] for k in want.files}, "golden arrays")
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4])
 def test_config2_cube256_1000_steps(F, golden, tmp_path, kernel):
     """BASELINE.json configs[1]: 256^3, computation mode, 1000 steps, bit-exact vs the reference."""
     g = golden.get("cube256_computation_1000")
@@ -212,7 +217,7 @@ def test_aggregate_matches_oracle(F, oracle):
                 assert bits_equal(ctx.aggregate(v), o.aggregate(q, f, v)), v
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4])
 @pytest.mark.parametrize("mode", [0, 1])
 def test_propagate_matches_reference_dumps(F, golden, tmp_path, mode, kernel):
     """fdtd_propagate == propagate_fields (main.c:755-799): same dump files, same variables in the
@@ -311,6 +316,36 @@ def test_random_shapes_and_launch_configs(F, oracle):
             variant.update(strip=2 if wx * wy > 8 else int(rng.integers(1, 3)), warps_x=wx, warps_y=wy,
                            stages=int(rng.integers(2, 7)))
         steps = int(rng.integers(1, 7))
+        q = to_oracle_params(oracle, p)
+        f = random_state(oracle, q, int(rng.integers(0, 1 << 30)))
+        with F.Context(p) as ctx:
+            configure(ctx, variant)
+            ctx.upload(upper(f))
+            t_gpu = ctx.run(steps, 0.0)
+            t_cpu = o.run(q, f, steps)
+            assert t_gpu == t_cpu
+            assert_fields_equal(ctx.download(), f, f"{(nx, ny, nz)} mode {mode} {variant} {steps} steps")
+        done += 1
+
+
+def test_two_step_kernel_random_shapes(F, oracle):
+    """kernel 4 (two time steps per sweep): 40 seeded random cavities x chunk length / block height /
+    ring depth, 1-9 steps from a random state, both modes: bit-exact against the oracle."""
+    o = oracle.restatement()
+    rng = np.random.default_rng(4242)
+    done = 0
+    while done < 40:
+        nx, ny, nz = (int(v) for v in rng.integers(1, 90, size=3))
+        mode = int(rng.integers(0, 2))
+        dims = ((nx + .5) * 1e-3, (ny + .5) * 1e-3, (nz + .5) * 1e-3)
+        p = F.make_params(*dims, 0.001, 6e-13, 1.2e-10, 2, mode)
+        if mode == 1:
+            plan = F.source_plan(p)
+            if plan.i0 < 0 or plan.j0 < 0 or plan.i1 > nx or plan.j1 > ny:
+                continue
+        variant = dict(kernel=4, kchunk=int(rng.choice([1, 2, 3, 4, 7, 32, 64, 1000])), warps_y=int(rng.choice([8, 12, 16])),
+                       stages=int(rng.integers(2, 6)))
+        steps = int(rng.integers(1, 10))
         q = to_oracle_params(oracle, p)
         f = random_state(oracle, q, int(rng.integers(0, 1 << 30)))
         with F.Context(p) as ctx:

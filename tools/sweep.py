@@ -21,6 +21,7 @@ ap.add_argument("--big", action="store_true")
 ap.add_argument("--fine", action="store_true")
 ap.add_argument("--tma", action="store_true")
 ap.add_argument("--prefetch", action="store_true")
+ap.add_argument("--step2", action="store_true", help="the two-steps-per-sweep kernel (4)")
 ap.add_argument("--only", type=int, default=None, help="only this kernel id (plus the one-thread-per-cell reference)")
 args = ap.parse_args()
 
@@ -62,6 +63,10 @@ if args.small:
     for kchunk, (wx, wy) in itertools.product((4, 8, 16, 32, 64), [(4, 2), (2, 2), (2, 4), (1, 8)]):
         variants.append(dict(kernel=3, strip=2 if (wx, wy) != (1, 8) else 1, kchunk=kchunk, stages=3 if (wx, wy) != (1, 8) else 4, warps_x=wx, warps_y=wy))
     variants.append(dict(kernel=1, strip=2, kchunk=8, warps_x=2, warps_y=2))
+if args.step2:
+    variants = [dict(kernel=0), dict(kernel=3, strip=1, kchunk=32, stages=4, warps_x=1, warps_y=8)]
+    for wy, stages, kchunk in itertools.product((8, 12, 16), (2, 3, 4), (32, 64, 128)):
+        variants.append(dict(kernel=4, warps_y=wy, stages=stages, kchunk=kchunk))
 if args.only is not None:
     variants = [v for v in variants if v["kernel"] == args.only or v["kernel"] == 0]
 
