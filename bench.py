@@ -350,7 +350,17 @@ def main():
     kopts = {k: ctx.get_option(k) for k in ("kernel", "strip", "kchunk", "warps_x", "warps_y", "stages")}
     kernel_id = kopts["kernel"]
     cap = traffic_for(kopts)
-    if kernel_id >= 2:
+    steps_per_launch = 1
+    if kernel_id == 4:
+        # ONE launch advances every cell by TWO time steps (an odd K ends with one single-step sweep)
+        steps_per_launch = 2
+        n_launch = (K + 1) // 2
+        dom_ms = h_ms / n_launch
+        dom_name = (f"k_step2_tma<{kopts['warps_y']}> (two time steps per sweep, TMA-staged, {kopts['stages']} stages, "
+                    f"{kopts['kchunk']} planes per block)")
+        alg_bytes = 2 * 2 * BYTES_PER_CELL_HALF_STEP * cells_local   # 144 B per cell-update, two of them
+        min_bytes = 96.0 * cells_local                               # six arrays in, six arrays out, once per sweep
+    elif kernel_id >= 2:
         # fused step: ONE launch advances every cell by a full time step (H and E)
         dom_ms = h_ms / K
         dom_name = (f"k_step_fused_tma<{kopts['strip']},{kopts['warps_x']},{kopts['warps_y']}> (H+E in one sweep, TMA-staged, "
@@ -369,16 +379,18 @@ def main():
                 "traffic_source": cap["source"] if cap else None,
                 "traffic_over_minimum": traffic / min_bytes if traffic else None,
                 "dram_gbs_from_traffic": traffic / (dom_ms * 1e-3) / 1e9 if traffic else None,
+                "dram_frac_of_peak": traffic / (dom_ms * 1e-3) / 1e9 / peak if traffic else None,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": dom_ms,
+                "time_steps_per_launch": steps_per_launch,
                 "bytes_per_cell_update_basis": 144,
-                "fused_minimum_bytes_per_launch": min_bytes,
-                "achieved_on_fused_minimum": min_bytes / (dom_ms * 1e-3) / 1e9,
-                "frac_on_fused_minimum": min_bytes / (dom_ms * 1e-3) / 1e9 / peak,
-                "note": ("achieved/frac use SURVEY.md 8(d)'s 144 B per cell-update (the split H + E half-steps); "
-                         "the fused sweep reads and writes each of the six arrays once per step = 96 B per "
-                         "cell-update, so frac can exceed 1: frac_on_fused_minimum is the HBM utilisation on the "
-                         "bytes the kernel has to move, dram_gbs_from_traffic on the bytes ncu saw it move"
-                         if kernel_id >= 2 else "two launches per step; 72 B per cell and half-step"),
+                "minimum_bytes_per_launch": min_bytes,
+                "achieved_on_minimum": min_bytes / (dom_ms * 1e-3) / 1e9,
+                "frac_on_minimum": min_bytes / (dom_ms * 1e-3) / 1e9 / peak,
+                "note": ("achieved/frac use SURVEY.md 8(d)'s 144 B per cell-update (the split H + E half-steps). A sweep "
+                         "that fuses H and E -- and here two whole time steps -- moves far fewer bytes per cell-update "
+                         "(48 B at best for two steps), so frac exceeds 1 by construction; the HBM utilisation is "
+                         "dram_frac_of_peak (bytes ncu saw the kernel move / its duration / peak) and frac_on_minimum "
+                         "(the bytes it cannot avoid)" if kernel_id >= 2 else "two launches per step; 72 B per cell and half-step"),
                 "step_frac_of_roofline": (2 * BYTES_PER_CELL_HALF_STEP * cells_local / (total_ms / K * 1e-3) / 1e9) / peak}
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------
@@ -518,23 +530,31 @@ def run_dumps50(args):
 # traffic = null -- never another kernel's bytes.
 _CELLS_NCU = 1024 * 1024 * 256
 TRAFFIC_TABLE = {
-    (1, 2, 2, 2, None): {"bytes_per_cell": 20.022561e9 / _CELLS_NCU,
-                         "source": "profiles/r01_split_ncu_full_raw.csv (k_update_h_march<2>, 20.02 GB per launch at 1024x1024x256)"},
-    (3, 2, 4, 2, 3): {"bytes_per_cell": (14.695572e9 + 12.960834e9) / _CELLS_NCU,
-                      "source": "profiles/r01_tma_ncu_full_raw.csv (k_step_fused_tma<2,4,2>, 128x4 tile, 3 stages: 14.70 GB read + "
-                                "12.96 GB written per launch at 1024x1024x256)"},
+    "k1_s2_wx2_wy2": {"bytes_per_cell": 20.022561e9 / _CELLS_NCU,
+                      "source": "profiles/r01_split_ncu_full_raw.csv (k_update_h_march<2>, 20.02 GB per launch at 1024x1024x256)"},
+    "k3_s2_wx4_wy2_st3": {"bytes_per_cell": (14.695572e9 + 12.960834e9) / _CELLS_NCU,
+                          "source": "profiles/r01_tma_ncu_full_raw.csv (k_step_fused_tma<2,4,2>, 128x4 tile, 3 stages: 14.70 GB read + "
+                                    "12.96 GB written per launch at 1024x1024x256)"},
 }
 try:
-    with open(os.path.join(ROOT, "profiles", "traffic_table.json")) as _fh:   # written by tools/ncu_traffic.py
+    with open(os.path.join(ROOT, "profiles", "traffic_table.json")) as _fh:   # written from tools/ncu_traffic.py output
         for _e in json.load(_fh):
-            TRAFFIC_TABLE[tuple(_e["key"])] = {"bytes_per_cell": _e["bytes_per_cell"], "source": _e["source"]}
-except (OSError, ValueError, KeyError):
+            TRAFFIC_TABLE[_e["key"]] = {"bytes_per_cell": _e["bytes_per_cell"], "source": _e["source"]}
+except (OSError, ValueError, KeyError, TypeError):
     pass
 
 
+def traffic_key(opts):
+    k = opts["kernel"]
+    if k == 4:     # the chunk length decides how much of the tile overlap L2 absorbs: part of the key
+        return f"k4_wy{opts['warps_y']}_st{opts['stages']}_kc{opts['kchunk']}"
+    if k == 3:
+        return f"k3_s{opts['strip']}_wx{opts['warps_x']}_wy{opts['warps_y']}_st{opts['stages']}"
+    return f"k{k}_s{opts['strip']}_wx{opts['warps_x']}_wy{opts['warps_y']}"
+
+
 def traffic_for(opts):
-    stages = opts["stages"] if opts["kernel"] == 3 else None
-    return TRAFFIC_TABLE.get((opts["kernel"], opts["strip"], opts["warps_x"], opts["warps_y"], stages))
+    return TRAFFIC_TABLE.get(traffic_key(opts))
 
 
 if __name__ == "__main__":

@@ -101,7 +101,7 @@ int copy_field(fdtd_ctx *c, int idx, double *host_first_owned_plane, bool to_dev
 Src make_src(const fdtd_ctx *c, const double *row)
 {
     Src s;
-    s.on = c->src_plane >= 0 ? 1 : 0;
+    s.on = c->src_staged ? 1 : 0;
     s.kl = c->src_plane;
     s.i0 = (int)c->plan.i0;
     s.i1 = (int)c->plan.i1;
@@ -124,7 +124,11 @@ Src no_src()
 template <int TY>
 void launch_h_march_t(const fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStream_t st)
 {
-    const int wx = (int)c->opt_wx, wy = (int)c->opt_wy;
+    int wx = (int)c->opt_wx, wy = (int)c->opt_wy;
+    if (wx * wy > 8) { /* the block shape belongs to another kernel (TMA kernels go up to 16 warps) */
+        wx = 2;
+        wy = 4;
+    }
     Span sp{kl_begin, kl_end, (int)c->opt_kchunk, (int)c->opt_prefetch};
     dim3 block(32 * wx, wy);
     dim3 grid((c->g.I + 1 + block.x - 1) / block.x, (c->g.J + 1 + wy * TY - 1) / (wy * TY),
@@ -136,7 +140,11 @@ void launch_h_march_t(const fdtd_ctx *c, const Src &s, int kl_begin, int kl_end,
 template <int TY>
 void launch_e_march_t(const fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStream_t st)
 {
-    const int wx = (int)c->opt_wx, wy = (int)c->opt_wy;
+    int wx = (int)c->opt_wx, wy = (int)c->opt_wy;
+    if (wx * wy > 8) { /* the block shape belongs to another kernel (TMA kernels go up to 16 warps) */
+        wx = 2;
+        wy = 4;
+    }
     Span sp{kl_begin, kl_end, (int)c->opt_kchunk, (int)c->opt_prefetch};
     dim3 block(32 * wx, wy);
     dim3 grid((c->g.I + 1 + block.x - 1) / block.x, (c->g.J + 1 + wy * TY - 1) / (wy * TY),
@@ -199,7 +207,8 @@ void launch_e(const fdtd_ctx *c, const Src &s, int kl_begin, int kl_end, cudaStr
  * (fdtd_fused.cuh): a thread of an edge block may read up to one row and one column before the
  * first array and up to two planes and a few rows past the last one.  Those values are never
  * used for a stored result; the margins only keep the addresses inside the allocation. */
-size_t margin_front(const fdtd_ctx *c) { return (size_t)c->g.P + 64; }
+/* (the front margin also holds the extra plane below array 0, see create_impl) */
+size_t margin_front(const fdtd_ctx *c) { return (size_t)c->g.P + 64 + (size_t)c->g.PR; }
 /* back: the unpredicated kernel (k_step_fused) reads, from an edge block of the last plane, up to
  * one plane plus a block's rows (at most 8 warps x 4 rows) plus a block's columns (256) further */
 size_t margin_back(const fdtd_ctx *c) { return 2 * (size_t)c->g.PR + 40 * (size_t)c->g.P + 2048; }
@@ -267,7 +276,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
 
-int encode_maps(fdtd_ctx *c, int bx, int by)
+int encode_maps(fdtd_ctx *c, int bx, int by, bool wide = false)
 {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
@@ -281,23 +290,30 @@ int encode_maps(fdtd_ctx *c, int bx, int by)
         encode = (EncodeTiledFn)fn;
     }
     double *sets[2] = {c->base, c->base2};
-    if (c->tma_bx == bx && c->tma_by == by && c->tma_base[0] == sets[0] && c->tma_base[1] == sets[1])
+    const bool same_shape = c->tma_bx == bx && c->tma_by == by && c->tma_promo == c->opt_l2promo && c->tma_wide == wide;
+    if (same_shape && c->tma_base[0] == sets[0] && c->tma_base[1] == sets[1])
         return FDTD_OK;
-    if (c->tma_bx == bx && c->tma_by == by && c->tma_base[0] == sets[1] && c->tma_base[1] == sets[0]) {
+    if (same_shape && c->tma_base[0] == sets[1] && c->tma_base[1] == sets[0]) {
         std::swap(c->tma_maps[0], c->tma_maps[1]); /* the two states swapped roles */
         std::swap(c->tma_base[0], c->tma_base[1]);
         return FDTD_OK;
     }
-    const cuuint64_t dims[3] = {(cuuint64_t)c->g.P, (cuuint64_t)c->g.R, (cuuint64_t)c->g.planes};
+    /* wide: the tensor starts at the spare plane below plane 0, so local plane kl is z = kl + 1 */
+    const cuuint64_t dims[3] = {(cuuint64_t)c->g.P, (cuuint64_t)c->g.R, (cuuint64_t)(c->g.planes + (wide ? 2 : 0))};
+    const size_t shift = wide ? (size_t)c->g.PR : 0;
     const cuuint64_t strides[2] = {(cuuint64_t)c->g.P * 8, (cuuint64_t)c->g.PR * 8};
     const cuuint32_t box[3] = {(cuuint32_t)(bx + 4), (cuuint32_t)(by + 2), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapL2promotion promo = c->opt_l2promo == 0   ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                         : c->opt_l2promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                         : c->opt_l2promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                               : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     for (int set = 0; set < 2; ++set)
         for (int a = 0; a < 6; ++a) {
             CUresult r = encode(&c->tma_maps[set].m[a], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
-                                sets[set] + (size_t)a * c->array_elems, dims, strides, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                sets[set] + (size_t)a * c->array_elems - shift, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) {
                 fdtd_set_error("cuTensorMapEncodeTiled failed with CUresult %d (box %d x %d)", (int)r, bx + 2, by + 2);
                 return FDTD_E_CUDA;
@@ -305,6 +321,8 @@ int encode_maps(fdtd_ctx *c, int bx, int by)
         }
     c->tma_bx = bx;
     c->tma_by = by;
+    c->tma_promo = (int)c->opt_l2promo;
+    c->tma_wide = wide;
     c->tma_base[0] = sets[0];
     c->tma_base[1] = sets[1];
     return FDTD_OK;
@@ -391,7 +409,7 @@ template <int WY>
 int launch_step2_t(fdtd_ctx *c, const Src &s1, const Src &s2, int kl_begin, int kl_end, cudaStream_t st)
 {
     constexpr int BYE = 2 * WY;
-    FDTD_TRY(encode_maps(c, kS2BoxW - 4, BYE - 1));
+    FDTD_TRY(encode_maps(c, kS2BoxW - 4, BYE - 1, true));
     /* as many stages as asked for, as far as the shared memory of one SM goes (at least two) */
     const size_t stage_bytes = (size_t)6 * tma_box_doubles(kS2BoxW - 4, BYE - 1) * sizeof(double);
     const int stages = (int)std::max(2L, std::min(c->opt_stages, (long)(200 * 1024 / stage_bytes)));
@@ -405,7 +423,7 @@ int launch_step2_t(fdtd_ctx *c, const Src &s1, const Src &s2, int kl_begin, int 
         if (c->n_smem_optin < 16)
             c->smem_optin[c->n_smem_optin++] = fn;
     }
-    Span sp{kl_begin, kl_end, (int)std::max(c->opt_kchunk, 4L), 0};
+    Span sp{kl_begin, kl_end, (int)std::max(c->opt_kchunk, 2L), 0, (int)c->opt_band};
     dim3 block(32, WY);
     dim3 grid((c->g.I + 1 + kS2TileX - 1) / kS2TileX, (c->g.J + 1 + BYE - 4) / (BYE - 3),
               (kl_end - kl_begin + sp.kchunk - 1) / sp.kchunk);
@@ -444,7 +462,7 @@ void launch_set_source(const fdtd_ctx *c, const double *row_dev, cudaStream_t st
  * then the interior planes; exchange_many(seg_xchg(seg), on_comm = true) then moves the boundary
  * planes on the halo streams while the interior planes run (fdtd_halo.cu).  The two are separate so
  * that one host thread can drive every slab of a group: all launches, then all transfers. */
-int seg_launch(fdtd_ctx *c, const Src &s, Segment seg)
+int seg_launch(fdtd_ctx *c, const Src &s, Segment seg, const Src *second)
 {
     FDTD_TRY(use_device(c));
     const int nk = c->g.nk;
@@ -453,7 +471,32 @@ int seg_launch(fdtd_ctx *c, const Src &s, Segment seg)
     const bool sends_up = c->rank + 1 < c->nranks, sends_down = c->rank > 0;
     if (multi)
         FDTD_TRY(wait_halos(c));
-    if (seg == SEG_FUSED) {
+    if (seg != SEG_STEP2)
+        c->wide_halo_valid = false; /* a single step refreshes one halo plane each way only */
+    if (seg == SEG_STEP2) {
+        /* two steps in one sweep: reads c->f (with two halo planes each way), writes c->f2, swap.
+         * The two planes at either end travel: they go first. */
+        if (!multi) {
+            FDTD_TRY(launch_step2(c, s, *second, 1, h_end, c->s_main));
+        } else if (nk < 6) {
+            FDTD_TRY(launch_step2(c, s, *second, 1, h_end, c->s_main));
+            CUDA_TRY(cudaEventRecord(c->ev_bnd, c->s_main));
+        } else {
+            int lo = 1, hi = h_end;
+            if (sends_up) {
+                FDTD_TRY(launch_step2(c, s, *second, nk - 1, nk + 1, c->s_main));
+                hi = nk - 1;
+            }
+            if (sends_down) {
+                FDTD_TRY(launch_step2(c, s, *second, 1, 3, c->s_main));
+                lo = 3;
+            }
+            CUDA_TRY(cudaEventRecord(c->ev_bnd, c->s_main));
+            FDTD_TRY(launch_step2(c, s, *second, lo, hi, c->s_main));
+        }
+        swap_buffers(c);
+        c->e_halo_valid = c->h_halo_valid = c->low_e_halo_valid = c->wide_halo_valid = true; /* after the exchange */
+    } else if (seg == SEG_FUSED) {
         /* reads c->f, writes c->f2, then the two swap */
         if (!multi) {
             launch_fused(c, s, 1, h_end, c->s_main);
@@ -517,11 +560,18 @@ int seg_launch(fdtd_ctx *c, const Src &s, Segment seg)
 Xchg seg_xchg(Segment seg)
 {
     Xchg x;
-    x.h = seg == SEG_FUSED || seg == SEG_H;
+    x.h = seg == SEG_FUSED || seg == SEG_H || seg == SEG_STEP2;
     x.h_with_e = seg == SEG_FUSED;
-    x.e = seg == SEG_FUSED || seg == SEG_E;
+    x.e = seg == SEG_FUSED || seg == SEG_E || seg == SEG_STEP2;
     x.e_with_hz = false;
+    x.wide = seg == SEG_STEP2;
     return x;
+}
+
+bool step2_usable(const fdtd_ctx *c)
+{
+    /* a slab must own the two planes it sends each way */
+    return c->nranks == 1 || c->p.maxk / (size_t)c->nranks >= 2;
 }
 
 /* One pass of the loop body main.c:770-779 for one context (one process per GPU). */
@@ -555,11 +605,11 @@ int stage_source_rows(fdtd_ctx *c, size_t count, double *t_io)
     CUDA_TRY(cudaEventSynchronize(c->ev_src)); /* previous upload has left the pinned buffer */
     double t = *t_io;
     for (size_t s = 0; s < count; ++s, t += c->p.time_step) {
-        if (c->src_plane >= 0)
+        if (c->src_staged)
             FDTD_TRY(fdtd_source_values(&c->p, &c->plan, t, c->src_host + s * row,
                                         c->src_host + s * row + c->src_n));
     }
-    if (c->src_plane >= 0 && row > 0) {
+    if (c->src_staged && row > 0) {
         CUDA_TRY(cudaMemcpyAsync(c->src_dev, c->src_host, count * row * sizeof(double),
                                  cudaMemcpyHostToDevice, c->s_main));
         CUDA_TRY(cudaEventRecord(c->ev_src, c->s_main));
@@ -626,7 +676,8 @@ int run_impl(fdtd_ctx *c, size_t steps, double *time_counter, float *total_ms, f
 {
     FDTD_TRY(use_device(c));
     FDTD_TRY(settle_kernel(c));
-    FDTD_TRY(refresh_halos_many(&c, 1, c->opt_kernel >= 2));
+    if (!(c->opt_kernel == 4 && step2_usable(c) && steps >= 2)) /* (the two-step kernel refreshes its wider halos itself) */
+        FDTD_TRY(refresh_halos_many(&c, 1, c->opt_kernel >= 2));
     const bool timed = total_ms != nullptr;
     const bool per_kernel = timed && (h_ms || e_ms);
     const size_t max_kernel_events = 2048;
@@ -658,14 +709,15 @@ int run_impl(fdtd_ctx *c, size_t steps, double *time_counter, float *total_ms, f
             const Src src = make_src(c, c->src_dev + s * row);
             const size_t gs = done + s;
             const bool ev = per_kernel && gs * 3 + 2 < evs.size();
-            if (c->opt_kernel == 4 && s + 1 < chunk) {
-                /* two steps in one sweep: reads c->f, writes c->f2, then the two swap */
+            if (c->opt_kernel == 4 && s + 1 < chunk && step2_usable(c)) {
+                /* two steps in one sweep */
                 const Src src2 = make_src(c, c->src_dev + (s + 1) * row);
                 const bool ev2 = per_kernel && (gs + 1) * 3 + 2 < evs.size();
+                FDTD_TRY(refresh_halos_many(&c, 1, true, true));
                 if (ev)
                     CUDA_TRY(cudaEventRecord(evs[3 * gs], c->s_main));
-                FDTD_TRY(launch_step2(c, src, src2, 1, c->g.nk + c->g.top + 1, c->s_main));
-                swap_buffers(c);
+                FDTD_TRY(seg_launch(c, src, SEG_STEP2, &src2));
+                FDTD_TRY(exchange_many(&c, 1, seg_xchg(SEG_STEP2), true));
                 CUDA_TRY(cudaGetLastError());
                 if (ev) { /* the sweep is booked on the first of its two steps */
                     CUDA_TRY(cudaEventRecord(evs[3 * gs + 1], c->s_main));
@@ -677,6 +729,8 @@ int run_impl(fdtd_ctx *c, size_t steps, double *time_counter, float *total_ms, f
                 ++s;
                 continue;
             }
+            if (c->opt_kernel == 4)
+                FDTD_TRY(refresh_halos_many(&c, 1, true)); /* a single step after pairs, or slabs too thin for pairs */
             if (ev)
                 FDTD_TRY(queue_step(c, src, evs[3 * gs], evs[3 * gs + 1], evs[3 * gs + 2]));
             else
@@ -767,7 +821,10 @@ int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx
     g.kbase = (int)c->k0;
     g.top = (rank == nranks - 1) ? 1 : 0;
     g.planes = g.nk + 2;
-    c->array_elems = (size_t)g.PR * (size_t)g.planes;
+    /* every array has one spare plane below local plane 0 and one above plane nk + 1: the second halo
+     * plane of the two-steps-per-sweep kernel (local planes -1 and nk + 2).  Everything else addresses
+     * planes 0 .. nk + 1 and never sees them. */
+    c->array_elems = (size_t)g.PR * (size_t)(g.planes + 2);
     /* launch-shape limits: the per-cell kernels put one plane per blockIdx.z, and the fused kernels
      * index inside a plane with 32-bit offsets */
     if (g.planes > 65535 || g.PR >= (1LL << 31) - 4 * (long long)g.P) {
@@ -778,17 +835,20 @@ int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx
     }
     c->ch = fdtd_factor_h(p);
     c->ce = fdtd_factor_e(p);
-    /* default: the TMA-staged fused step with the launch shape that won the sweeps on a B200 at
-     * 256^3, 512^3 and 1024^3 (profiles/): 32 x 8 tile, one row per thread, 32 planes per block,
-     * 4 stages in flight */
-    c->opt_kernel = 3;
+    /* default: two time steps per sweep over the TMA ring (fdtd_step2_tma.cuh) with the launch shape that
+     * won the sweeps on a B200 (profiles/r02_sweep_step2_*): 28 x 13 stored sites per block of 32 x 8
+     * threads, 32 planes per block, 3 stages in flight.  An odd step, and slabs thinner than two
+     * planes, take the single-step TMA sweep (32 x 8 tile, 4 stages). */
+    c->opt_kernel = 4;
     c->kernel_auto = true;
     c->opt_strip = 1;
     c->opt_kchunk = 32;
     c->opt_wx = 1;
     c->opt_wy = 8;
-    c->opt_stages = 4;
+    c->opt_stages = 3;
     c->opt_prefetch = 3;
+    c->opt_band = 1;
+    c->opt_l2promo = 3;
     c->opt_host_chunk = 0; /* automatic */
     c->opt_host_pipeline = 1;
 
@@ -799,7 +859,8 @@ int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx
     }
     c->src_n = 0;
     c->src_here = false;
-    c->src_plane = -1;
+    c->src_staged = false;
+    c->src_plane = 0;
     if (p->mode == 1) {
         /* the reference writes the patch without a bounds check (main.c:745-752); outside the
          * grid that is undefined behaviour there and an error here */
@@ -812,7 +873,8 @@ int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx
         }
         c->src_n = (int)(c->plan.i1 - c->plan.i0);
         c->src_here = (c->k0 == 0);
-        c->src_plane = c->k0 == 0 ? 1 : (c->k0 == 1 ? 0 : -1);
+        c->src_staged = c->k0 <= 2; /* k0 = 1, 2: the plane is a halo plane that gets H recomputed here */
+        c->src_plane = 1 - (int)c->k0;
     }
 
 #define CREATE_TRY(expr)                                                                       \
@@ -850,7 +912,7 @@ int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx
     CREATE_TRY(cudaEventRecord(c->ev_src, c->s_main));
     CREATE_TRY(cudaStreamSynchronize(c->s_main));
 #undef CREATE_TRY
-    c->e_halo_valid = c->h_halo_valid = c->low_e_halo_valid = true; /* all zero: halos agree */
+    c->e_halo_valid = c->h_halo_valid = c->low_e_halo_valid = c->wide_halo_valid = true; /* all zero: halos agree */
     *out = c;
     return FDTD_OK;
 }
@@ -915,14 +977,17 @@ int fdtd_ctx_set_option(fdtd_ctx *c, const char *key, long value)
         return FDTD_E_ARG;
     }
     if (!strcmp(key, "kernel") && value >= 0 && value <= 4) {
-        if (value == 4 && c->nranks > 1) {
-            fdtd_set_error("fdtd_ctx_set_option: kernel 4 (two steps per sweep) runs on single-slab contexts only");
-            return FDTD_E_ARG;
-        }
-        if (value == 4 && c->opt_kernel != 4) { /* its own launch defaults */
+        if (value == 4 && c->opt_kernel != 4) { /* its own launch defaults (profiles/r02_sweep_step2_*) */
             c->opt_wy = 8;
             c->opt_stages = 3;
-            c->opt_kchunk = 64;
+            c->opt_kchunk = 32;
+        }
+        if (value == 3 && c->opt_kernel == 4) { /* and the single-step TMA sweep's */
+            c->opt_strip = 1;
+            c->opt_wx = 1;
+            c->opt_wy = 8;
+            c->opt_stages = 4;
+            c->opt_kchunk = 32;
         }
         c->opt_kernel = value;
         c->kernel_auto = false;
@@ -933,6 +998,8 @@ int fdtd_ctx_set_option(fdtd_ctx *c, const char *key, long value)
     else if (!strcmp(key, "warps_x") && value >= 1 && value <= 8) c->opt_wx = value;
     else if (!strcmp(key, "warps_y") && value >= 1 && value <= (c->opt_kernel == 4 ? 16 : 8)) c->opt_wy = value;
     else if (!strcmp(key, "prefetch") && value >= 0 && value <= 64) c->opt_prefetch = value;
+    else if (!strcmp(key, "band") && value >= 1 && value <= 1024) c->opt_band = value;
+    else if (!strcmp(key, "l2promo") && value >= 0 && value <= 3) c->opt_l2promo = value;
     else if (!strcmp(key, "host_chunk") && value >= 0 && value <= 1 << 20) c->opt_host_chunk = value;
     else if (!strcmp(key, "host_pipeline") && value >= 0 && value <= 1) c->opt_host_pipeline = value;
     else {
@@ -956,6 +1023,8 @@ int fdtd_ctx_get_option(fdtd_ctx *c, const char *key, long *value)
     else if (!strcmp(key, "warps_y")) *value = c->opt_wy;
     else if (!strcmp(key, "prefetch")) *value = c->opt_prefetch;
     else if (!strcmp(key, "stages")) *value = c->opt_stages;
+    else if (!strcmp(key, "band")) *value = c->opt_band;
+    else if (!strcmp(key, "l2promo")) *value = c->opt_l2promo;
     else if (!strcmp(key, "host_chunk")) *value = c->opt_host_chunk;
     else if (!strcmp(key, "host_pipeline")) *value = c->opt_host_pipeline;
     else if (!strcmp(key, "k0")) *value = (long)c->k0;
@@ -1007,7 +1076,7 @@ static int upload_impl(fdtd_ctx *c, const fdtd_fields *host, bool whole_cavity)
     double *h[6] = {host->Ex, host->Ey, host->Ez, host->Hx, host->Hy, host->Hz};
     for (int a = 0; a < 6; ++a)
         FDTD_TRY(copy_field(c, a, h[a] + slab_offset(c, a, whole_cavity), true));
-    c->e_halo_valid = c->h_halo_valid = c->low_e_halo_valid = (c->nranks == 1);
+    c->e_halo_valid = c->h_halo_valid = c->low_e_halo_valid = c->wide_halo_valid = (c->nranks == 1);
     return FDTD_OK;
 }
 
@@ -1049,7 +1118,7 @@ int fdtd_set_initial_conditions(fdtd_ctx *c)
         rc = FDTD_E_CUDA;
     }
     free(ey);
-    c->e_halo_valid = c->low_e_halo_valid = (c->nranks == 1);
+    c->e_halo_valid = c->low_e_halo_valid = c->wide_halo_valid = (c->nranks == 1);
     return rc;
 }
 
@@ -1062,7 +1131,7 @@ int fdtd_set_source(fdtd_ctx *c, double t)
         return FDTD_E_STATE;
     }
     if (c->nranks > 1)
-        c->h_halo_valid = c->low_e_halo_valid = false; /* plane k = 0 may be a plane that travels (same on all ranks) */
+        c->h_halo_valid = c->low_e_halo_valid = c->wide_halo_valid = false; /* plane k = 0 may be a plane that travels (same on all ranks) */
     if (!c->src_here)
         return FDTD_OK; /* the patch lives on the slab that holds k = 0 */
     FDTD_TRY(wait_halos(c));
@@ -1084,7 +1153,7 @@ int fdtd_update_H_field(fdtd_ctx *c)
     FDTD_TRY(wait_halos(c));
     launch_h(c, no_src(), 1, c->g.nk + c->g.top + 1, c->s_main);
     CUDA_TRY(cudaGetLastError());
-    c->h_halo_valid = (c->nranks == 1);
+    c->h_halo_valid = c->wide_halo_valid = (c->nranks == 1);
     return FDTD_OK;
 }
 
@@ -1096,7 +1165,7 @@ int fdtd_update_E_field(fdtd_ctx *c)
     FDTD_TRY(wait_halos(c));
     launch_e(c, no_src(), 1, c->g.nk + 1, c->s_main);
     CUDA_TRY(cudaGetLastError());
-    c->e_halo_valid = c->low_e_halo_valid = (c->nranks == 1);
+    c->e_halo_valid = c->low_e_halo_valid = c->wide_halo_valid = (c->nranks == 1);
     return FDTD_OK;
 }
 

@@ -87,6 +87,7 @@ struct Xchg {
     bool h_with_e; /*   ... and Ex, Ey, Ez of that plane (fused step) */
     bool e;        /* Ex, Ey of my first node plane -> plane nk+1 of rank-1 */
     bool e_with_hz;/*   ... and Hz (dump variables only) */
+    bool wide;     /* instead: two planes of all six arrays each way (two-step kernel); needs h and e */
 };
 
 struct DumpPipe;
@@ -103,7 +104,7 @@ struct fdtd_ctx {
     double *base2;      /* second set for the fused single-sweep step ("kernel" = 2), allocated on demand */
     double *raw, *raw2; /* what cudaMalloc returned */
     Fld f2;
-    size_t array_elems; /* P * R * planes */
+    size_t array_elems; /* stride between the six arrays: P * R * (planes + 2), see create_impl */
     double ch, ce;      /* update factors, main.c:441 / :479 */
 
     cudaStream_t s_main, s_comm, s_dump;
@@ -112,6 +113,7 @@ struct fdtd_ctx {
     cudaEvent_t ev_sent;            /* TR_FLAG: my pushes have left my planes */
     bool e_halo_valid, h_halo_valid;
     bool low_e_halo_valid; /* fused step only: plane 0 also holds the lower neighbour's Ex, Ey, Ez */
+    bool wide_halo_valid;  /* two-step kernel: planes -1, 0, nk+1, nk+2 of all six arrays are current */
     ncclComm_t comm;
     bool has_comm;
     bool in_group;      /* slab of an fdtd_group: calls that exchange halos go through the group */
@@ -134,21 +136,23 @@ struct fdtd_ctx {
     fdtd_source_plan plan;
     int src_n;          /* points per row */
     bool src_here;      /* computation mode and this slab holds k = 0 */
-    int src_plane;      /* local index of the global plane k = 0 if a kernel of this slab touches it, else -1 */
+    bool src_staged;    /* a kernel of this slab touches the global plane k = 0 (it owns it, or recomputes it as halo) */
+    int src_plane;      /* local index of that plane: 1, 0 or -1 */
     double *src_dev;    /* kSrcRing rows of 2*src_n doubles */
     double *src_host;   /* pinned mirror */
     cudaEvent_t ev_src; /* last upload of the ring finished */
     double *src_one_dev; /* single row for the operator-level fdtd_set_source */
 
     /* options */
-    long opt_kernel, opt_strip, opt_kchunk, opt_wx, opt_wy, opt_prefetch, opt_stages;
+    long opt_kernel, opt_strip, opt_kchunk, opt_wx, opt_wy, opt_prefetch, opt_stages, opt_band, opt_l2promo;
     long opt_host_chunk, opt_host_pipeline; /* fdtd_run_hosted: planes per z-chunk (0 = automatic), 0/1 */
     cudaStream_t s_h2d;                     /* uploads of fdtd_run_hosted (created on first use) */
 
     /* tensor maps of the TMA-staged fused step: [buffer set][array], valid for tma_bx x tma_by tiles */
     TmaMaps tma_maps[2];
     double *tma_base[2];
-    int tma_bx, tma_by;
+    int tma_bx, tma_by, tma_promo;
+    bool tma_wide;
     const void *smem_optin[16]; /* kernels already opted in to large dynamic shared memory on this device */
     int n_smem_optin;
     mutable long launches; /* kernels of this library launched so far (reports) */
@@ -198,13 +202,15 @@ int exchange_many(fdtd_ctx *const *cs, int n, const Xchg &x, bool on_comm);
  * sent have been read: before any kernel that reads halo planes or overwrites owned ones */
 int wait_halos(fdtd_ctx *c);
 /* bring the halos the selected kernels need up to date (after uploads and operator-level calls) */
-int refresh_halos_many(fdtd_ctx *const *cs, int n, bool fused);
+int refresh_halos_many(fdtd_ctx *const *cs, int n, bool fused, bool wide = false);
 void halo_destroy(fdtd_ctx *c);
 int alloc_sig(fdtd_ctx *c);
 
 /* a step is made of segments: one for the fused kernels, two for the split ones (see fdtd_ctx.cu) */
-enum Segment { SEG_FUSED, SEG_H, SEG_E };
-int seg_launch(fdtd_ctx *c, const fdtd::Src &s, Segment seg);
+enum Segment { SEG_FUSED, SEG_H, SEG_E, SEG_STEP2 };
+int seg_launch(fdtd_ctx *c, const fdtd::Src &s, Segment seg, const fdtd::Src *second = nullptr);
+/* the two-step kernel can serve this cavity's slabs (every slab at least two planes thick) */
+bool step2_usable(const fdtd_ctx *c);
 Xchg seg_xchg(Segment seg);
 
 /* one context, optionally timed (one process per GPU) */

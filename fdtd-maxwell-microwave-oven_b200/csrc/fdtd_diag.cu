@@ -141,7 +141,7 @@ int fdtd_fill_test_pattern(fdtd_ctx *c, unsigned long long seed)
         k_fill_pattern<<<grid, block, 0, c->s_main>>>(c->g, field_ptr(c, a), v, seed, a);
     }
     CUDA_TRY(cudaGetLastError());
-    c->e_halo_valid = c->h_halo_valid = c->low_e_halo_valid = (c->nranks == 1);
+    c->e_halo_valid = c->h_halo_valid = c->low_e_halo_valid = c->wide_halo_valid = (c->nranks == 1);
     return FDTD_OK;
 }
 

@@ -61,7 +61,9 @@ static int group_run(fdtd_ctx *const *cs, int n, size_t steps, double *time_coun
             want_fused = false;
         }
     }
-    FDTD_TRY(refresh_halos_many(cs, n, want_fused));
+    const bool pairs = want_fused && cs[0]->opt_kernel == 4 && step2_usable(cs[0]);
+    if (!(pairs && steps >= 2))
+        FDTD_TRY(refresh_halos_many(cs, n, want_fused));
 
     const Segment fused_plan[1] = {SEG_FUSED}, split_plan[2] = {SEG_H, SEG_E};
     const Segment *plan = want_fused ? fused_plan : split_plan;
@@ -76,6 +78,20 @@ static int group_run(fdtd_ctx *const *cs, int n, size_t steps, double *time_coun
             FDTD_TRY(stage_source_rows(cs[r], chunk, &t_chunk));
         }
         for (size_t s = 0; s < chunk; ++s) {
+            if (pairs && s + 1 < chunk) { /* two steps in one sweep on every slab */
+                FDTD_TRY(refresh_halos_many(cs, n, true, true));
+                for (int r = 0; r < n; ++r) {
+                    fdtd_ctx *c = cs[r];
+                    const size_t row = 2 * (size_t)c->src_n;
+                    const fdtd::Src s1 = make_src(c, c->src_dev + s * row), s2 = make_src(c, c->src_dev + (s + 1) * row);
+                    FDTD_TRY(seg_launch(c, s1, SEG_STEP2, &s2));
+                }
+                FDTD_TRY(exchange_many(cs, n, seg_xchg(SEG_STEP2), true));
+                ++s;
+                continue;
+            }
+            if (pairs)
+                FDTD_TRY(refresh_halos_many(cs, n, true));
             for (int g = 0; g < nseg; ++g) {
                 for (int r = 0; r < n; ++r) {
                     fdtd_ctx *c = cs[r];

@@ -137,30 +137,41 @@ int alloc_sig(fdtd_ctx *c)
 
 /* ---- what travels ----------------------------------------------------------------------------- */
 
-/* arrays of the upward exchange in the order they are sent: Hx, Hy (+ Ex, Ey, Ez) */
-static int up_arrays(const Fld &f, bool with_e, double *out[5])
+/* One direction of an exchange: `count` arrays (indices into Ex Ey Ez Hx Hy Hz), `planes` consecutive
+ * planes starting at the sender's local plane `src`, landing at the receiver's local plane `dst`
+ * (dst may be -1: the spare plane below plane 0). */
+struct Lane {
+    int count, arrays[6];
+    int planes, src, dst;
+};
+
+/* upward: from a slab with nk_sender cell planes into the slab above it */
+static Lane up_lane(const Xchg &x, int nk_sender)
 {
-    out[0] = f.hx; out[1] = f.hy; out[2] = f.ex; out[3] = f.ey; out[4] = f.ez;
-    return with_e ? 5 : 2;
+    Lane l;
+    if (x.wide) { /* two-step kernel: the top two owned planes of everything -> planes -1, 0 */
+        l = Lane{6, {0, 1, 2, 3, 4, 5}, 2, nk_sender - 1, -1};
+    } else {      /* Hx, Hy (+ Ex, Ey, Ez for the fused step) of the top owned plane -> plane 0 */
+        l = Lane{x.h_with_e ? 5 : 2, {3, 4, 0, 1, 2, 0}, 1, nk_sender, 0};
+    }
+    return l;
 }
 
-/* arrays of the downward exchange: Ex, Ey (+ Hz) */
-static int down_arrays(const Fld &f, bool with_hz, double *out[3])
+/* downward: from a slab into the slab below it, which has nk_receiver cell planes */
+static Lane down_lane(const Xchg &x, int nk_receiver)
 {
-    out[0] = f.ex; out[1] = f.ey; out[2] = f.hz;
-    return with_hz ? 3 : 2;
+    Lane l;
+    if (x.wide) { /* the first two owned planes of everything -> planes nk + 1, nk + 2 */
+        l = Lane{6, {0, 1, 2, 3, 4, 5}, 2, 1, nk_receiver + 1};
+    } else {      /* Ex, Ey (+ Hz for dumps) of the first owned plane -> plane nk + 1 */
+        l = Lane{x.e_with_hz ? 3 : 2, {0, 1, 5, 0, 0, 0}, 1, 1, nk_receiver + 1};
+    }
+    return l;
 }
 
-static Fld fld_of(double *base, size_t array_elems)
+static double *plane_ptr(double *base, size_t array_elems, long long PR, int array, int plane)
 {
-    Fld f;
-    f.ex = base;
-    f.ey = base + array_elems;
-    f.ez = base + 2 * array_elems;
-    f.hx = base + 3 * array_elems;
-    f.hy = base + 4 * array_elems;
-    f.hz = base + 5 * array_elems;
-    return f;
+    return base + (size_t)array * array_elems + (long long)plane * PR; /* plane -1 is the spare plane */
 }
 
 /* TR_NCCL: the sends and receives of one slab (inside the caller's NCCL group) */
@@ -170,27 +181,31 @@ static int nccl_exchange(fdtd_ctx *c, cudaStream_t st, const Xchg &x)
         fdtd_set_error("multi-rank context without communicator: call fdtd_ctx_comm_init first");
         return FDTD_E_STATE;
     }
-    const size_t n = (size_t)c->g.PR;
+    const long long PR = c->g.PR;
     const bool up = c->rank + 1 < c->nranks, lo = c->rank > 0;
     if (x.h) {
-        double *a[5];
-        const int cnt = up_arrays(c->f, x.h_with_e, a);
+        const Lane l = up_lane(x, c->g.nk);
+        const size_t n = (size_t)PR * l.planes;
         if (up)
-            for (int i = 0; i < cnt; ++i)
-                NCCL_TRY(g_nccl.Send(a[i] + n * c->g.nk, n, ncclDouble, c->rank + 1, c->comm, st));
+            for (int i = 0; i < l.count; ++i)
+                NCCL_TRY(g_nccl.Send(plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.src), n, ncclDouble,
+                                     c->rank + 1, c->comm, st));
         if (lo)
-            for (int i = 0; i < cnt; ++i)
-                NCCL_TRY(g_nccl.Recv(a[i], n, ncclDouble, c->rank - 1, c->comm, st));
+            for (int i = 0; i < l.count; ++i)
+                NCCL_TRY(g_nccl.Recv(plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.dst), n, ncclDouble,
+                                     c->rank - 1, c->comm, st));
     }
     if (x.e) {
-        double *a[3];
-        const int cnt = down_arrays(c->f, x.e_with_hz, a);
+        const Lane l = down_lane(x, c->g.nk); /* as receiver: my own nk */
+        const size_t n = (size_t)PR * l.planes;
         if (lo)
-            for (int i = 0; i < cnt; ++i)
-                NCCL_TRY(g_nccl.Send(a[i] + n, n, ncclDouble, c->rank - 1, c->comm, st));
+            for (int i = 0; i < l.count; ++i)
+                NCCL_TRY(g_nccl.Send(plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.src), n, ncclDouble,
+                                     c->rank - 1, c->comm, st));
         if (up)
-            for (int i = 0; i < cnt; ++i)
-                NCCL_TRY(g_nccl.Recv(a[i] + n * (c->g.nk + 1), n, ncclDouble, c->rank + 1, c->comm, st));
+            for (int i = 0; i < l.count; ++i)
+                NCCL_TRY(g_nccl.Recv(plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.dst), n, ncclDouble,
+                                     c->rank + 1, c->comm, st));
     }
     return FDTD_OK;
 }
@@ -198,24 +213,24 @@ static int nccl_exchange(fdtd_ctx *c, cudaStream_t st, const Xchg &x)
 /* TR_EVENT: this slab pulls what its neighbours hold for it */
 static int event_pull(fdtd_ctx *c, cudaStream_t st, const Xchg &x)
 {
-    const size_t n = (size_t)c->g.PR, bytes = n * sizeof(double);
+    const long long PR = c->g.PR;
     if (x.h && c->nb_lo) {
         fdtd_ctx *s = c->nb_lo;
         CUDA_TRY(cudaStreamWaitEvent(st, s->ev_bnd, 0));
-        double *src[5], *dst[5];
-        const int cnt = up_arrays(s->f, x.h_with_e, src);
-        up_arrays(c->f, x.h_with_e, dst);
-        for (int i = 0; i < cnt; ++i)
-            CUDA_TRY(cudaMemcpyPeerAsync(dst[i], c->device, src[i] + n * s->g.nk, s->device, bytes, st));
+        const Lane l = up_lane(x, s->g.nk);
+        for (int i = 0; i < l.count; ++i)
+            CUDA_TRY(cudaMemcpyPeerAsync(plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.dst), c->device,
+                                         plane_ptr(s->base, s->array_elems, PR, l.arrays[i], l.src), s->device,
+                                         (size_t)PR * l.planes * sizeof(double), st));
     }
     if (x.e && c->nb_hi) {
         fdtd_ctx *s = c->nb_hi;
         CUDA_TRY(cudaStreamWaitEvent(st, s->ev_bnd, 0));
-        double *src[3], *dst[3];
-        const int cnt = down_arrays(s->f, x.e_with_hz, src);
-        down_arrays(c->f, x.e_with_hz, dst);
-        for (int i = 0; i < cnt; ++i)
-            CUDA_TRY(cudaMemcpyPeerAsync(dst[i] + n * (c->g.nk + 1), c->device, src[i] + n, s->device, bytes, st));
+        const Lane l = down_lane(x, c->g.nk);
+        for (int i = 0; i < l.count; ++i)
+            CUDA_TRY(cudaMemcpyPeerAsync(plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.dst), c->device,
+                                         plane_ptr(s->base, s->array_elems, PR, l.arrays[i], l.src), s->device,
+                                         (size_t)PR * l.planes * sizeof(double), st));
     }
     return FDTD_OK;
 }
@@ -223,19 +238,19 @@ static int event_pull(fdtd_ctx *c, cudaStream_t st, const Xchg &x)
 /* TR_FLAG: this slab pushes into its neighbours' halo planes */
 static int flag_push(fdtd_ctx *c, cudaStream_t st, const Xchg &x)
 {
-    const size_t n = (size_t)c->g.PR, bytes = n * sizeof(double);
+    const long long PR = c->g.PR;
     const bool up = c->rank + 1 < c->nranks, lo = c->rank > 0;
     if (x.h) {
         const unsigned seq = ++c->n_xh;
-        if (lo) /* everything that read the previous content of my plane 0 precedes this point of `st` */
+        if (lo) /* everything that read the previous content of my lower halo precedes this point of `st` */
             FDTD_TRY(flag_post(c, st, c->peer_sig_lo + SIG_UP_ACK, seq - 1));
         if (up) {
             FDTD_TRY(flag_wait(c, st, c->sig + SIG_UP_ACK, seq - 1));
-            double *src[5], *dst[5];
-            const int cnt = up_arrays(c->f, x.h_with_e, src);
-            up_arrays(fld_of(c->peer_hi[c->flip], c->peer_elems_hi), x.h_with_e, dst);
-            for (int i = 0; i < cnt; ++i)
-                CUDA_TRY(cudaMemcpyAsync(dst[i], src[i] + n * c->g.nk, bytes, cudaMemcpyDefault, st));
+            const Lane l = up_lane(x, c->g.nk);
+            for (int i = 0; i < l.count; ++i)
+                CUDA_TRY(cudaMemcpyAsync(plane_ptr(c->peer_hi[c->flip], c->peer_elems_hi, PR, l.arrays[i], l.dst),
+                                         plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.src),
+                                         (size_t)PR * l.planes * sizeof(double), cudaMemcpyDefault, st));
             FDTD_TRY(flag_post(c, st, c->peer_sig_hi + SIG_UP_DATA, seq));
         }
     }
@@ -245,11 +260,11 @@ static int flag_push(fdtd_ctx *c, cudaStream_t st, const Xchg &x)
             FDTD_TRY(flag_post(c, st, c->peer_sig_hi + SIG_DOWN_ACK, seq - 1));
         if (lo) {
             FDTD_TRY(flag_wait(c, st, c->sig + SIG_DOWN_ACK, seq - 1));
-            double *src[3], *dst[3];
-            const int cnt = down_arrays(c->f, x.e_with_hz, src);
-            down_arrays(fld_of(c->peer_lo[c->flip], c->peer_elems_lo), x.e_with_hz, dst);
-            for (int i = 0; i < cnt; ++i)
-                CUDA_TRY(cudaMemcpyAsync(dst[i] + n * (size_t)(c->peer_nk_lo + 1), src[i] + n, bytes, cudaMemcpyDefault, st));
+            const Lane l = down_lane(x, c->peer_nk_lo);
+            for (int i = 0; i < l.count; ++i)
+                CUDA_TRY(cudaMemcpyAsync(plane_ptr(c->peer_lo[c->flip], c->peer_elems_lo, PR, l.arrays[i], l.dst),
+                                         plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.src),
+                                         (size_t)PR * l.planes * sizeof(double), cudaMemcpyDefault, st));
             FDTD_TRY(flag_post(c, st, c->peer_sig_lo + SIG_DOWN_DATA, seq));
         }
     }
@@ -349,12 +364,24 @@ int exchange_many(fdtd_ctx *const *cs, int n, const Xchg &x, bool on_comm)
 }
 
 /* The validity flags are set identically on every slab, so the transfers always pair up. */
-int refresh_halos_many(fdtd_ctx *const *cs, int n, bool fused)
+int refresh_halos_many(fdtd_ctx *const *cs, int n, bool fused, bool wide)
 {
     fdtd_ctx *c0 = cs[0];
     if (c0->nranks == 1)
         return FDTD_OK;
+    if (wide) { /* the two-step kernel's halos: two planes of everything, both ways */
+        if (c0->wide_halo_valid)
+            return FDTD_OK;
+        Xchg w;
+        w.h = w.e = w.wide = true;
+        w.h_with_e = w.e_with_hz = false;
+        FDTD_TRY(exchange_many(cs, n, w, false));
+        for (int r = 0; r < n; ++r) /* planes 0 and nk + 1 of every array are current as well */
+            cs[r]->wide_halo_valid = cs[r]->e_halo_valid = cs[r]->h_halo_valid = cs[r]->low_e_halo_valid = true;
+        return FDTD_OK;
+    }
     Xchg x;
+    x.wide = false;
     x.e = !c0->e_halo_valid;
     x.e_with_hz = false;
     x.h = !c0->h_halo_valid || (fused && !c0->low_e_halo_valid);
@@ -595,8 +622,8 @@ int fdtd_ctx_peer_connect(fdtd_ctx *c, const void *blobs)
     for (int r = 0; r < c->nranks; ++r) {
         memcpy(&all[r], (const char *)blobs + (size_t)r * FDTD_PEER_BLOB_BYTES, sizeof(PeerBlob));
         const PeerBlob &b = all[r];
-        if (b.magic != kBlobMagic || b.rank != r || b.nranks != c->nranks || b.array_elems / (size_t)(b.nk + 2) !=
-                                                                                 c->array_elems / (size_t)(c->g.nk + 2)) {
+        if (b.magic != kBlobMagic || b.rank != r || b.nranks != c->nranks || b.array_elems / (size_t)(b.nk + 4) !=
+                                                                                 c->array_elems / (size_t)(c->g.nk + 4)) {
             fdtd_set_error("fdtd_ctx_peer_connect: entry %d is not the export of rank %d of this cavity", r, r);
             return FDTD_E_ARG;
         }

@@ -94,7 +94,7 @@ __device__ __forceinline__ void step2_sweep(const Geo &g, const TmaMaps &maps, c
         tma::mbar_expect_tx(bar, full_bytes);
 #pragma unroll
         for (int a = 0; a < 6; ++a)
-            tma::load_box(dst + a * box, &maps.m[a], X0 - 2, Y0 - 2, plane, bar);
+            tma::load_box(dst + a * box, &maps.m[a], X0 - 2, Y0 - 2, plane + 1, bar); /* the maps start at plane -1 */
     };
     if (leader)
         for (int n = 0; n < stages && n < nplanes; ++n)
@@ -136,8 +136,10 @@ __device__ __forceinline__ void step2_sweep(const Geo &g, const TmaMaps &maps, c
         const double *sex = cur, *sey = cur + box, *sez = cur + 2 * box;
         const double *shx = cur + 3 * box, *shy = cur + 4 * box, *shz = cur + 5 * box;
         const int gk = k - 1 + g.kbase;                     /* global index of plane k */
-        const bool cell1 = k <= g.nk, kin1 = gk >= 1 && cell1;
-        const bool cell2 = k - 1 <= g.nk, kin2 = gk - 1 >= 1 && cell2;
+        /* by GLOBAL plane: a halo plane of a slab is an ordinary plane of the cavity; only the cavity's top
+         * node plane K has no cells */
+        const bool cell1 = gk < g.K, kin1 = gk >= 1 && cell1;
+        const bool cell2 = gk - 1 < g.K, kin2 = gk - 1 >= 1 && cell2;
         const bool srck1 = s1.on && k == s1.kl;             /* stage A/B work on the source plane */
         const bool srck2 = s2.on && k - 1 == s2.kl;         /* stage C/D do */
 
@@ -318,8 +320,22 @@ k_step2_tma(Geo g, const __grid_constant__ TmaMaps maps, Fld b, double cH, doubl
     double *ring = reinterpret_cast<double *>(smem_raw);
 
     constexpr int BYE = 2 * WY;
-    const int X0 = blockIdx.x * kS2TileX;
-    const int Y0 = blockIdx.y * (BYE - 3);
+    /* Which tile?  Blocks start in the order of their linear index, a few hundred at a time, and sweep
+     * upward at the same pace: two blocks share the halo of their tiles through L2 only if they start
+     * close together.  Row-major order puts the tile above a whole row of tiles (37 at 1024^3) later,
+     * too far for L2; so tiles are numbered column by column inside bands of sp.band tile rows --
+     * then both the tile above and the tile to the right start within a few blocks. */
+    int tx = blockIdx.x, ty = blockIdx.y;
+    if (sp.band > 1) {
+        const int nx = gridDim.x, ny = gridDim.y;
+        const int lin = blockIdx.x + nx * blockIdx.y;
+        const int band = lin / (sp.band * nx), rem = lin - band * sp.band * nx;
+        const int rows = min(sp.band, ny - band * sp.band);
+        tx = rem / rows;
+        ty = band * sp.band + rem - tx * rows;
+    }
+    const int X0 = tx * kS2TileX;
+    const int Y0 = ty * (BYE - 3);
     const int kl0 = sp.kl_begin + blockIdx.z * sp.kchunk;
     const int kl1 = min(kl0 + sp.kchunk, sp.kl_end);
 

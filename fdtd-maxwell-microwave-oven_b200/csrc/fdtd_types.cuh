@@ -75,6 +75,7 @@ struct Span {
     int kl_begin, kl_end; /* local planes [kl_begin, kl_end) handled by this launch */
     int kchunk;           /* planes per block */
     int prefetch;         /* planes ahead to pull into L2 (0 = off) */
+    int band;             /* two-step kernel: tiles are handed out column by column inside bands of this many tile rows */
 };
 
 /* non-blocking hint: bring the line holding p into L2 (no register, no scoreboard entry) */

@@ -34,7 +34,8 @@ def layouts(worlds=(2, 3, 4, 8)):
     return out
 
 
-VARIANTS = [dict(kernel=3, strip=2, kchunk=4, warps_x=2, warps_y=2, stages=3),
+VARIANTS = [dict(kernel=4, kchunk=4, warps_y=8, stages=2),
+            dict(kernel=3, strip=2, kchunk=4, warps_x=2, warps_y=2, stages=3),
             dict(kernel=2, strip=1, kchunk=32, warps_x=1, warps_y=4),
             dict(kernel=1, strip=2, kchunk=3, warps_x=2, warps_y=2),
             dict(kernel=0)]
@@ -148,13 +149,14 @@ def test_group_default_kernel_when_the_last_block_holds_one_column(F, oracle, di
             assert bits_equal(got[k[0].upper() + k[1:]], want), (world, k)
 
 
-@pytest.mark.parametrize("kernel", [3, 1])
-def test_many_short_runs_back_to_back_on_thin_slabs(F, oracle, kernel):
+@pytest.mark.parametrize("nz", [6, 13])
+@pytest.mark.parametrize("kernel", [4, 3, 1])
+def test_many_short_runs_back_to_back_on_thin_slabs(F, oracle, kernel, nz):
     """Queue many short runs without synchronising in between, on slabs of one or two planes: every
     run must see the halos the previous one sent (the exchange of run n is still in flight when the
     host queues run n + 1)."""
     o = oracle.restatement()
-    dims = (70, 45, 6)
+    dims = (70, 45, nz)
     args = tuple((d + .5) * 1e-3 for d in dims) + (0.001, 6e-13, 1.2e-10, 2, 1)
     p, q = F.make_params(*args), oracle.make_params(*args)
     assert p.dims() == dims
@@ -163,10 +165,11 @@ def test_many_short_runs_back_to_back_on_thin_slabs(F, oracle, kernel):
         with F.Group(p, world, devices=devices, transport=transport) as g:
             g.set_option("kernel", kernel)
             g.upload(upper(f))
-            t = 0.0
-            for _ in range(40):
-                t = g.run(1, t)
-            t_cpu = o.run(q, f, 40)
+            t, total = 0.0, 0
+            for n in range(20):
+                t = g.run(1 + n % 3, t)          # 1, 2, 3, 1, ... steps: single sweeps and two-step sweeps mixed
+                total += 1 + n % 3
+            t_cpu = o.run(q, f, total)
             assert t == t_cpu
             got = g.download()
         for k, want in f.items():

@@ -118,11 +118,16 @@ CASES = [((37, 28, 23), 1, 7, dict(kernel=1, strip=2, kchunk=8, warps_x=2, warps
          ((40, 33, 4), 1, 5, dict(kernel=2, strip=4, kchunk=16, warps_x=1, warps_y=2)),
          ((37, 28, 23), 1, 7, dict(kernel=3, strip=2, kchunk=8, warps_x=2, warps_y=2, stages=3)),
          ((70, 21, 8), 0, 6, dict(kernel=3, strip=1, kchunk=100, warps_x=1, warps_y=4, stages=4)),
-         ((64, 21, 11), 1, 6, dict())]      # defaults; the last block in x holds the single column i = I
+         ((64, 21, 11), 1, 6, dict()),      # defaults; the last block in x holds the single column i = I
+         # two steps per sweep: two halo planes each way, odd and even step counts, slabs of 2..3 planes
+         ((37, 28, 23), 1, 7, dict(kernel=4, kchunk=8)),
+         ((70, 21, 8), 0, 6, dict(kernel=4, kchunk=3, warps_y=12, stages=2)),
+         ((33, 40, 9), 1, 8, dict(kernel=4, kchunk=1000, warps_y=16)),
+         ((40, 33, 4), 1, 5, dict(kernel=4))]   # slabs too thin for the wide halos: single-step sweeps
 
 
 if os.environ.get("FDTD_MULTI_QUICK") == "1":  # a short list for expensive many-GPU boxes
-    CASES = [CASES[0], CASES[4], CASES[8], CASES[9]]
+    CASES = [CASES[0], CASES[4], CASES[8], CASES[9], CASES[11], CASES[12]]
 
 
 def _spawn(target, world, *args):

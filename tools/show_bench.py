@@ -16,7 +16,7 @@ for line in open(sys.argv[1]):
     print(" config:", d["config"].get("workload", "")[:60], d["config"].get("kernel"), d["config"].get("transport"),
           "fallback" if d["config"].get("fallback") else "")
     print(" roofline: frac144=%.3f frac96=%s traffic/min=%s dram=%s" % (
-        r.get("frac", 0), r.get("frac_on_fused_minimum"), r.get("traffic_over_minimum"), r.get("dram_gbs_from_traffic")))
+        r.get("frac", 0), r.get("frac_on_minimum"), r.get("traffic_over_minimum"), r.get("dram_gbs_from_traffic")))
     print(" e2e:", e.get("value"), e.get("seconds"), e.get("matches_selfcheck"), e.get("skipped"))
     print(" selfcheck:", d.get("selfcheck"))
     print(" cpu:", (d.get("cpu_baseline") or {}).get("value"), " clocks:", d.get("clocks"))

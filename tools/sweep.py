@@ -65,8 +65,10 @@ if args.small:
     variants.append(dict(kernel=1, strip=2, kchunk=8, warps_x=2, warps_y=2))
 if args.step2:
     variants = [dict(kernel=0), dict(kernel=3, strip=1, kchunk=32, stages=4, warps_x=1, warps_y=8)]
-    for wy, stages, kchunk in itertools.product((8, 12, 16), (2, 3, 4), (32, 64, 128)):
-        variants.append(dict(kernel=4, warps_y=wy, stages=stages, kchunk=kchunk))
+    for wy, kchunk, promo in itertools.product((8, 16), (16, 24, 32, 48, 64), (0, 2, 3)):
+        variants.append(dict(kernel=4, warps_y=wy, stages=3, kchunk=kchunk, l2promo=promo))
+    for promo in (0, 2, 3):
+        variants.append(dict(kernel=3, strip=1, kchunk=32, stages=4, warps_x=1, warps_y=8, l2promo=promo))
 if args.only is not None:
     variants = [v for v in variants if v["kernel"] == args.only or v["kernel"] == 0]
 
@@ -84,6 +86,8 @@ with F.Context(p) as ctx:
         t = ctx.run(2, 0.0)
         ctx.sync()
         t, total, h, e = ctx.run_timed(args.steps, t)
+        t, total2, h, e = ctx.run_timed(args.steps, t)
+        total = min(total, total2)
         s = ctx.checksum()
         if ref_sum is None:
             ref_sum = s
