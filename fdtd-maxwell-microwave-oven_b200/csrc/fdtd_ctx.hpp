@@ -187,6 +187,7 @@ int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx
 int copy_planes(fdtd_ctx *c, int idx, double *host_first_owned_plane, int kl0, int kl1, bool to_device, cudaStream_t st);
 int copy_field(fdtd_ctx *c, int idx, double *host_first_owned_plane, bool to_device);
 void launch_fused(fdtd_ctx *c, const fdtd::Src &s, int kl_begin, int kl_end, cudaStream_t st);
+int launch_step2(fdtd_ctx *c, const fdtd::Src &s1, const fdtd::Src &s2, int kl_begin, int kl_end, cudaStream_t st);
 void swap_buffers(fdtd_ctx *c);
 int settle_kernel(fdtd_ctx *c);
 int ensure_pong(fdtd_ctx *c);

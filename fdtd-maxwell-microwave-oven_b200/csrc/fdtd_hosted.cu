@@ -44,14 +44,18 @@ static double *host_array(const fdtd_fields *h, int idx)
     return a[idx];
 }
 
-/* steps [s_first, s_last] (1-based, of this call) as a wavefront; the state before step s_first is
- * c->f.  upload: chunk u's planes arrive from `host` first (then s_first must be 1);
- * download: each chunk leaves for `host` after its step s_last.  On return c->f is the final state. */
-static int wavefront(fdtd_ctx *c, const fdtd_fields *host, const Chunks &ch, int nsteps, bool upload, bool download,
+/* `nsteps` time steps as a wavefront; the state before them is c->f.  upload: chunk u's planes
+ * arrive from `host` first; download: each chunk leaves for `host` after its last step.  With the
+ * two-step kernel a wave element is a sweep of TWO steps (an odd count ends with a single-step sweep);
+ * the dependency pattern is the same, a sweep reaches two planes into the neighbouring chunks and
+ * chunks are at least two planes thick.  On return c->f is the final state. */
+static int wavefront(fdtd_ctx *c, const fdtd_fields *host, const Chunks &ch, int nsteps_in, bool upload, bool download,
                      const double *src_rows)
 {
     const int M = ch.count;
     const size_t row = 2 * (size_t)c->src_n;
+    const bool pairs = c->opt_kernel == 4;
+    const int nsteps = pairs ? (nsteps_in + 1) / 2 : nsteps_in; /* sweeps */
     std::vector<cudaEvent_t> ev_up(upload ? M : 0), ev_done(download ? M : 0);
     for (auto &e : ev_up)
         CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -82,7 +86,15 @@ static int wavefront(fdtd_ctx *c, const fdtd_fields *host, const Chunks &ch, int
                 swap_buffers(c);
                 parity ^= 1;
             }
-            launch_fused(c, make_src(c, src_rows + (size_t)(s - 1) * row), ch.begin(k), ch.end(k), c->s_main);
+            if (pairs && 2 * s <= nsteps_in) {
+                const int rc2 = launch_step2(c, make_src(c, src_rows + (size_t)(2 * s - 2) * row),
+                                             make_src(c, src_rows + (size_t)(2 * s - 1) * row), ch.begin(k), ch.end(k), c->s_main);
+                if (rc2 != FDTD_OK)
+                    c->launch_error = rc2;
+            } else {
+                const int step = pairs ? nsteps_in : s; /* the odd last step of a two-step run */
+                launch_fused(c, make_src(c, src_rows + (size_t)(step - 1) * row), ch.begin(k), ch.end(k), c->s_main);
+            }
             if (c->launch_error != FDTD_OK) {
                 rc = c->launch_error;
                 c->launch_error = FDTD_OK;
