@@ -482,14 +482,18 @@ int seg_launch(fdtd_ctx *c, const Src &s, Segment seg, const Src *second)
             FDTD_TRY(launch_step2(c, s, *second, 1, h_end, c->s_main));
             CUDA_TRY(cudaEventRecord(c->ev_bnd, c->s_main));
         } else {
+            /* The chunk at either end of the slab goes first -- whole chunks, so that no plane is loaded
+             * more often than in a single launch (a chunk brings its own two planes of run-in anyway);
+             * the halo planes travel while the chunks in between run. */
+            const int bc = (int)std::min((long)std::max(2, nk / 4), std::max(c->opt_kchunk, 2L));
             int lo = 1, hi = h_end;
             if (sends_up) {
-                FDTD_TRY(launch_step2(c, s, *second, nk - 1, nk + 1, c->s_main));
-                hi = nk - 1;
+                FDTD_TRY(launch_step2(c, s, *second, h_end - bc, h_end, c->s_main));
+                hi = h_end - bc;
             }
             if (sends_down) {
-                FDTD_TRY(launch_step2(c, s, *second, 1, 3, c->s_main));
-                lo = 3;
+                FDTD_TRY(launch_step2(c, s, *second, 1, 1 + bc, c->s_main));
+                lo = 1 + bc;
             }
             CUDA_TRY(cudaEventRecord(c->ev_bnd, c->s_main));
             FDTD_TRY(launch_step2(c, s, *second, lo, hi, c->s_main));

@@ -124,13 +124,18 @@ int fdtd_ctx_peer_connect(fdtd_ctx *ctx, const void *blobs /* nranks x FDTD_PEER
  *   "kernel"   0 = one thread per cell (the plain operators, source as separate launches);
  *              1 = z-marching register strips, one H and one E launch per step, in place;
  *              2 = H and E fused into one sweep per step (needs the state twice in HBM);
- *              3 = the same sweep with operands staged by TMA into a shared-memory ring (default);
+ *              3 = the same sweep with operands staged by TMA into a shared-memory ring;
+ *              4 = TWO time steps per sweep over the TMA ring (default); an odd step and
+ *                  slabs thinner than two planes take the single-step sweep of kernel 3.
  *              Left at its default the context falls back to kernel 1 -- with a line on stderr and
  *              "fallback" = 1 -- when the second copy of the state does not fit; a kernel chosen
- *              explicitly fails with FDTD_E_NOMEM instead.
- *   "strip"    rows per thread (1..4);  "kchunk" planes per block;  "warps_x", "warps_y" block shape in
- *              warps (at most 8 warps; 16 for kernel 3);  "stages" depth of the TMA ring (2..8, kernel 3);
- *              "prefetch" planes of L2 prefetch ahead of the sweep (kernel 2).
+ *              explicitly fails with FDTD_E_NOMEM instead.  On slabs, choose the kernel before wiring.
+ *   "kchunk"   planes per block;  "stages" depth of the TMA ring (kernels 3, 4);
+ *   "warps_y"  kernel 4: block = 32 x warps_y threads storing 28 x (2 warps_y - 3) sites (8, 12, 16);
+ *   "strip", "warps_x", "warps_y" kernels 1-3: rows per thread (1..4) and block shape in warps (at most 8
+ *              warps; 16 for kernel 3);  "prefetch" planes of L2 prefetch ahead of the sweep (kernel 2);
+ *   "band", "l2promo"  measurement knobs of kernel 4 (tile numbering, TMA L2 promotion);
+ *   "host_chunk", "host_pipeline"  fdtd_run_hosted (below).
  * Read-only: "k0", "k1" (owned cell planes), "launches" (kernels launched by this library so far),
  *   "fallback" (1 after the automatic fallback), "fused_ok" (second state copy available on every slab),
  *   "transport" (0 none, 1 NCCL, 2 peer copies of a group, 3 peer memory with flags). */
@@ -155,7 +160,7 @@ int fdtd_update_H_field(fdtd_ctx *ctx);                  /* update_H_field(), ma
 int fdtd_update_E_field(fdtd_ctx *ctx);                  /* update_E_field(), main.c:469-500 */
 
 /* `steps` passes of the loop body main.c:770-779 (source, H, source, E) with the source and the
- * PEC walls fused into the two update kernels.  *time_counter is advanced by repeated addition
+ * PEC walls fused into the update kernels (by default two passes per kernel launch).  *time_counter is advanced by repeated addition
  * of time_step, as at main.c:765.  Asynchronous: returns once the work is queued. */
 int fdtd_run(fdtd_ctx *ctx, size_t steps, double *time_counter);
 /* Same, bracketed by CUDA events on the context's stream; blocks until done.
