@@ -428,7 +428,34 @@ int launch_step2_t(fdtd_ctx *c, const Src &s1, const Src &s2, int kl_begin, int 
     dim3 grid((c->g.I + 1 + kS2TileX - 1) / kS2TileX, (c->g.J + 1 + BYE - 4) / (BYE - 3),
               (kl_end - kl_begin + sp.kchunk - 1) / sp.kchunk);
     Src2 src{s1, s2};
-    k_step2_tma<WY><<<grid, block, smem, st>>>(c->g, c->tma_maps[0], c->f2, c->ch, c->ce, src, sp, stages);
+    const unsigned cx = (unsigned)c->opt_cluster_x, cy = (unsigned)c->opt_cluster_y;
+    if (cx * cy > 8) {
+        fdtd_set_error("two-step kernel: cluster_x (%u) * cluster_y (%u) must be <= 8", cx, cy);
+        return FDTD_E_ARG;
+    }
+    if (cx * cy > 1) {
+        /* Thread-block clusters: the blocks of a cluster are co-scheduled on one GPC and start together,
+         * so neighbouring tiles sweep z in step and L2 serves the halo they share.  The grid is padded to
+         * whole clusters; blocks whose tile lies outside the cavity leave at once. */
+        grid.x = (grid.x + cx - 1) / cx * cx;
+        grid.y = (grid.y + cy - 1) / cy * cy;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = grid;
+        cfg.blockDim = block;
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = cx;
+        attr.val.clusterDim.y = cy;
+        attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, k_step2_tma<WY>, c->g, c->tma_maps[0], c->f2, c->ch, c->ce, src, sp, stages));
+    } else {
+        k_step2_tma<WY><<<grid, block, smem, st>>>(c->g, c->tma_maps[0], c->f2, c->ch, c->ce, src, sp, stages);
+    }
     ++c->launches;
     return FDTD_OK;
 }
@@ -563,7 +590,7 @@ int seg_launch(fdtd_ctx *c, const Src &s, Segment seg, const Src *second)
 
 Xchg seg_xchg(Segment seg)
 {
-    Xchg x;
+    Xchg x{};
     x.h = seg == SEG_FUSED || seg == SEG_H || seg == SEG_STEP2;
     x.h_with_e = seg == SEG_FUSED;
     x.e = seg == SEG_FUSED || seg == SEG_E || seg == SEG_STEP2;
@@ -853,6 +880,7 @@ int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx
     c->opt_prefetch = 3;
     c->opt_band = 1;
     c->opt_l2promo = 3;
+    c->opt_cluster_x = c->opt_cluster_y = 1;
     c->opt_host_chunk = 0; /* automatic */
     c->opt_host_pipeline = 1;
 
@@ -1004,6 +1032,8 @@ int fdtd_ctx_set_option(fdtd_ctx *c, const char *key, long value)
     else if (!strcmp(key, "prefetch") && value >= 0 && value <= 64) c->opt_prefetch = value;
     else if (!strcmp(key, "band") && value >= 1 && value <= 1024) c->opt_band = value;
     else if (!strcmp(key, "l2promo") && value >= 0 && value <= 3) c->opt_l2promo = value;
+    else if (!strcmp(key, "cluster_x") && value >= 1 && value <= 8) c->opt_cluster_x = value;
+    else if (!strcmp(key, "cluster_y") && value >= 1 && value <= 8) c->opt_cluster_y = value;
     else if (!strcmp(key, "host_chunk") && value >= 0 && value <= 1 << 20) c->opt_host_chunk = value;
     else if (!strcmp(key, "host_pipeline") && value >= 0 && value <= 1) c->opt_host_pipeline = value;
     else {
@@ -1029,6 +1059,8 @@ int fdtd_ctx_get_option(fdtd_ctx *c, const char *key, long *value)
     else if (!strcmp(key, "stages")) *value = c->opt_stages;
     else if (!strcmp(key, "band")) *value = c->opt_band;
     else if (!strcmp(key, "l2promo")) *value = c->opt_l2promo;
+    else if (!strcmp(key, "cluster_x")) *value = c->opt_cluster_x;
+    else if (!strcmp(key, "cluster_y")) *value = c->opt_cluster_y;
     else if (!strcmp(key, "host_chunk")) *value = c->opt_host_chunk;
     else if (!strcmp(key, "host_pipeline")) *value = c->opt_host_pipeline;
     else if (!strcmp(key, "k0")) *value = (long)c->k0;

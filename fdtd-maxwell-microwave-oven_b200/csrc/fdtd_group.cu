@@ -28,8 +28,7 @@ int exchange_many_for_dump(fdtd_ctx *const *cs, int n)
 {
     if (cs[0]->nranks == 1)
         return FDTD_OK;
-    Xchg x;
-    x.h = x.h_with_e = false;
+    Xchg x{};
     x.e = x.e_with_hz = true;
     for (int r = 0; r < n; ++r)
         cs[r]->e_halo_valid = false;

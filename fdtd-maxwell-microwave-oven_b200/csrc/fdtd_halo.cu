@@ -372,18 +372,15 @@ int refresh_halos_many(fdtd_ctx *const *cs, int n, bool fused, bool wide)
     if (wide) { /* the two-step kernel's halos: two planes of everything, both ways */
         if (c0->wide_halo_valid)
             return FDTD_OK;
-        Xchg w;
+        Xchg w{};
         w.h = w.e = w.wide = true;
-        w.h_with_e = w.e_with_hz = false;
         FDTD_TRY(exchange_many(cs, n, w, false));
         for (int r = 0; r < n; ++r) /* planes 0 and nk + 1 of every array are current as well */
             cs[r]->wide_halo_valid = cs[r]->e_halo_valid = cs[r]->h_halo_valid = cs[r]->low_e_halo_valid = true;
         return FDTD_OK;
     }
-    Xchg x;
-    x.wide = false;
+    Xchg x{};
     x.e = !c0->e_halo_valid;
-    x.e_with_hz = false;
     x.h = !c0->h_halo_valid || (fused && !c0->low_e_halo_valid);
     x.h_with_e = fused;
     if (!x.e && !x.h)

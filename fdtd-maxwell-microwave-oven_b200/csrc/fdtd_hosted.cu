@@ -56,7 +56,18 @@ static int wavefront(fdtd_ctx *c, const fdtd_fields *host, const Chunks &ch, int
     const size_t row = 2 * (size_t)c->src_n;
     const bool pairs = c->opt_kernel == 4;
     const int nsteps = pairs ? (nsteps_in + 1) / 2 : nsteps_in; /* sweeps */
-    std::vector<cudaEvent_t> ev_up(upload ? M : 0), ev_done(download ? M : 0);
+    struct Events { /* destroyed on every way out */
+        std::vector<cudaEvent_t> v;
+        ~Events()
+        {
+            for (cudaEvent_t e : v)
+                if (e)
+                    cudaEventDestroy(e);
+        }
+    } ups, dones;
+    ups.v.assign(upload ? M : 0, nullptr);
+    dones.v.assign(download ? M : 0, nullptr);
+    std::vector<cudaEvent_t> &ev_up = ups.v, &ev_done = dones.v;
     for (auto &e : ev_up)
         CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &e : ev_done)
@@ -125,10 +136,6 @@ static int wavefront(fdtd_ctx *c, const fdtd_fields *host, const Chunks &ch, int
         if (cudaEventRecord(e, c->s_dump) != cudaSuccess || cudaStreamWaitEvent(c->s_main, e, 0) != cudaSuccess)
             rc = FDTD_E_CUDA;
     }
-    for (auto &e : ev_up)
-        cudaEventDestroy(e);
-    for (auto &e : ev_done)
-        cudaEventDestroy(e);
     if (rc == FDTD_E_CUDA)
         fdtd_set_error("fdtd_run_hosted: %s", cudaGetErrorString(cudaGetLastError()));
     return rc;

@@ -338,6 +338,8 @@ k_step2_tma(Geo g, const __grid_constant__ TmaMaps maps, Fld b, double cH, doubl
     const int Y0 = ty * (BYE - 3);
     const int kl0 = sp.kl_begin + blockIdx.z * sp.kchunk;
     const int kl1 = min(kl0 + sp.kchunk, sp.kl_end);
+    if (X0 > g.I || Y0 > g.J)
+        return; /* padding of a grid rounded up to whole clusters */
 
     if (threadIdx.x == 0 && threadIdx.y == 0) {
         for (int st = 0; st < stages; ++st)
