@@ -409,7 +409,7 @@ def main():
                    "skipped": f"{world} rank(s) x {need / 1e9:.1f} GB of pinned host buffers do not fit the "
                               f"{avail / 1e9:.0f} GB of host memory available on this node"}
         else:
-            host = F.PinnedArrays(p, shapes=shapes)
+            host = F.PinnedArrays(p, shapes=shapes, device=local)   # pages from the NUMA node of this rank's GPU
             ctx.fill_test_pattern(7)
             ctx.download_slab(host.arrays)          # synthetic input now lives in HOST memory
             barrier()
@@ -432,6 +432,7 @@ def main():
                    "h2d_bytes_per_step": need * world / K, "d2h_bytes_per_step": need * world / K,
                    "seconds": dt, "what": what + "; pinned host arrays in the reference's dense layout, wall clock, "
                                                  "max over ranks",
+                   "host_numa": dict(F.host_numa_info(local), policy=os.environ.get("FDTD_B200_HOST_NUMA", "near")),
                    "checksum_after": None}
             if not args.no_selfcheck:
                 # the pipelined path must leave the same state in the host arrays as the plain one

@@ -121,6 +121,8 @@ SIGNATURES = {
     "fdtd_fill_test_pattern": (C.c_int, [_CTX, C.c_ulonglong]),
     "fdtd_checksum": (C.c_int, [_CTX, C.POINTER(C.c_ulonglong)]),
     "fdtd_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "fdtd_host_alloc_near": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "fdtd_host_numa_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "fdtd_host_free": (C.c_int, [C.c_void_p]),
     "fdtd_ctx_info": (C.c_int, [_CTX, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
                                 C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
@@ -196,6 +198,12 @@ def slab_range(maxk, rank, nranks):
     return int(k0.value), int(k1.value)
 
 
+def host_numa_info(device=0):
+    nodes, node = C.c_int(), C.c_int()
+    _check(lib.fdtd_host_numa_info(int(device), C.byref(nodes), C.byref(node)))
+    return {"nodes": int(nodes.value), "node_of_device": int(node.value)}
+
+
 def nccl_unique_id() -> bytes:
     buf = C.create_string_buffer(128)
     _check(lib.fdtd_nccl_unique_id(buf))
@@ -224,13 +232,17 @@ HALO_PLAN_FUSED = {
 class PinnedArrays:
     """Six pinned host arrays in the reference's dense layout (fdtd_host_alloc)."""
 
-    def __init__(self, p, fill=None, shapes=None):
+    def __init__(self, p, fill=None, shapes=None, device=None):
+        """device: allocate near that GPU (fdtd_host_alloc_near)"""
         self._ptrs = []
         self.arrays = {}
         for name, shape in (shapes or field_shapes(p)).items():
             n = int(np.prod(shape))
             ptr = C.c_void_p()
-            _check(lib.fdtd_host_alloc(max(n, 1) * 8, C.byref(ptr)))
+            if device is None:
+                _check(lib.fdtd_host_alloc(max(n, 1) * 8, C.byref(ptr)))
+            else:
+                _check(lib.fdtd_host_alloc_near(int(device), max(n, 1) * 8, C.byref(ptr)))
             self._ptrs.append(ptr)
             buf = (C.c_double * n).from_address(ptr.value)
             arr = np.frombuffer(buf, dtype=np.float64).reshape(shape)

@@ -10,6 +10,9 @@
  */
 #include "fdtd_ctx.hpp"
 #include "fdtd_update.cuh"
+#include <cctype>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include "fdtd_fused.cuh"
 #include "fdtd_fused_tma.cuh"
 #include "fdtd_step2_tma.cuh"
@@ -460,12 +463,72 @@ int launch_step2_t(fdtd_ctx *c, const Src &s1, const Src &s2, int kl_begin, int 
     return FDTD_OK;
 }
 
+/* the persistent, warp-specialised form (k_step2_tma_ws): WYC compute warps + one producer warp per
+ * block, as many blocks as the GPU holds at once, rounds of tiles, planes-completed counters */
+template <int WYC>
+int launch_step2_ws_t(fdtd_ctx *c, const Src &s1, const Src &s2, int kl_begin, int kl_end, cudaStream_t st)
+{
+    constexpr int BYE = 2 * WYC;
+    FDTD_TRY(encode_maps(c, kS2BoxW - 4, BYE - 1, true));
+    const size_t stage_bytes = (size_t)6 * tma_box_doubles(kS2BoxW - 4, BYE - 1) * sizeof(double);
+    const int stages = (int)std::max(2L, std::min(c->opt_stages, (long)(200 * 1024 / stage_bytes)));
+    const size_t smem = (size_t)stages * stage_bytes;
+    const void *fn = (const void *)k_step2_tma_ws<WYC>;
+    bool configured = false;
+    for (int k = 0; k < c->n_smem_optin; ++k)
+        configured = configured || c->smem_optin[k] == fn;
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(k_step2_tma_ws<WYC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if (c->n_smem_optin < 16)
+            c->smem_optin[c->n_smem_optin++] = fn;
+    }
+    dim3 block(32, WYC + 1);
+    const int tiles_x = (c->g.I + 1 + kS2TileX - 1) / kS2TileX, tiles_y = (c->g.J + 1 + BYE - 4) / (BYE - 3);
+    int per_sm = 0, sms = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step2_tma_ws<WYC>, 32 * (WYC + 1), smem));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    const int tiles = tiles_x * tiles_y;
+    int nb = std::min(tiles, std::max(1, per_sm * sms));
+    if (nb > tiles_x) /* whole rows of tiles per round: the x overlap stays inside a round */
+        nb = nb / tiles_x * tiles_x;
+    const int rounds = (tiles + nb - 1) / nb;
+    const int planes = kl_end - kl_begin + 6;
+    const size_t need = (size_t)rounds * planes;
+    if (c->progress_elems < need) {
+        if (c->progress_dev) cudaFree(c->progress_dev);
+        c->progress_dev = nullptr;
+        c->progress_elems = 0;
+        CUDA_TRY(cudaMalloc((void **)&c->progress_dev, need * sizeof(unsigned)));
+        c->progress_elems = need;
+    }
+    CUDA_TRY(cudaMemsetAsync(c->progress_dev, 0, need * sizeof(unsigned), st));
+    Span sp{kl_begin, kl_end, kl_end - kl_begin, 0, 1};
+    sp.tiles_x = tiles_x;
+    sp.tiles_y = tiles_y;
+    sp.progress = c->progress_dev;
+    sp.progress_stride = planes;
+    sp.window = (int)c->opt_window;
+    Geo g = c->g;
+    TmaMaps maps = c->tma_maps[0];
+    Fld out = c->f2;
+    double ch = c->ch, ce = c->ce;
+    Src2 src{s1, s2};
+    int stg = stages;
+    void *args[] = {&g, &maps, &out, &ch, &ce, &src, &sp, &stg};
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(nb), block, args, smem, st));
+    ++c->launches;
+    return FDTD_OK;
+}
+
 int launch_step2(fdtd_ctx *c, const Src &s1, const Src &s2, int kl_begin, int kl_end, cudaStream_t st)
 {
     if (kl_end <= kl_begin)
         return FDTD_OK;
     int rc;
-    if (c->opt_wy >= 16)
+    if (c->opt_persistent)
+        rc = c->opt_wy > 8 ? launch_step2_ws_t<15>(c, s1, s2, kl_begin, kl_end, st)
+                           : launch_step2_ws_t<7>(c, s1, s2, kl_begin, kl_end, st);
+    else if (c->opt_wy >= 16)
         rc = launch_step2_t<16>(c, s1, s2, kl_begin, kl_end, st);
     else if (c->opt_wy >= 12)
         rc = launch_step2_t<12>(c, s1, s2, kl_begin, kl_end, st);
@@ -881,6 +944,8 @@ int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx
     c->opt_band = 1;
     c->opt_l2promo = 3;
     c->opt_cluster_x = c->opt_cluster_y = 1;
+    c->opt_persistent = 0;
+    c->opt_window = 4;
     c->opt_host_chunk = 0; /* automatic */
     c->opt_host_pipeline = 1;
 
@@ -987,6 +1052,7 @@ int fdtd_ctx_destroy(fdtd_ctx *c)
     if (c->src_one_dev) cudaFree(c->src_one_dev);
     if (c->src_host) cudaFreeHost(c->src_host);
     if (c->agg_dev) cudaFree(c->agg_dev);
+    if (c->progress_dev) cudaFree(c->progress_dev);
     cudaEvent_t evs[] = {c->ev_bnd, c->ev_sent, c->ev_hhalo, c->ev_ehalo, c->ev_src};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
@@ -1032,6 +1098,8 @@ int fdtd_ctx_set_option(fdtd_ctx *c, const char *key, long value)
     else if (!strcmp(key, "prefetch") && value >= 0 && value <= 64) c->opt_prefetch = value;
     else if (!strcmp(key, "band") && value >= 1 && value <= 1024) c->opt_band = value;
     else if (!strcmp(key, "l2promo") && value >= 0 && value <= 3) c->opt_l2promo = value;
+    else if (!strcmp(key, "persistent") && value >= 0 && value <= 1) c->opt_persistent = value;
+    else if (!strcmp(key, "window") && value >= 1 && value <= 64) c->opt_window = value;
     else if (!strcmp(key, "cluster_x") && value >= 1 && value <= 8) c->opt_cluster_x = value;
     else if (!strcmp(key, "cluster_y") && value >= 1 && value <= 8) c->opt_cluster_y = value;
     else if (!strcmp(key, "host_chunk") && value >= 0 && value <= 1 << 20) c->opt_host_chunk = value;
@@ -1059,6 +1127,8 @@ int fdtd_ctx_get_option(fdtd_ctx *c, const char *key, long *value)
     else if (!strcmp(key, "stages")) *value = c->opt_stages;
     else if (!strcmp(key, "band")) *value = c->opt_band;
     else if (!strcmp(key, "l2promo")) *value = c->opt_l2promo;
+    else if (!strcmp(key, "persistent")) *value = c->opt_persistent;
+    else if (!strcmp(key, "window")) *value = c->opt_window;
     else if (!strcmp(key, "cluster_x")) *value = c->opt_cluster_x;
     else if (!strcmp(key, "cluster_y")) *value = c->opt_cluster_y;
     else if (!strcmp(key, "host_chunk")) *value = c->opt_host_chunk;
@@ -1235,18 +1305,105 @@ int fdtd_sync(fdtd_ctx *c)
     CUDA_TRY(cudaStreamSynchronize(c->s_dump));
     return FDTD_OK;
 }
-int fdtd_host_alloc(size_t bytes, void **out)
+/* NUMA placement of pinned host buffers.  On a two-socket 8-GPU box every rank streams ~50 GB each way
+ * through its buffers; if they all sit on one socket, the GPUs of the other one pull them across the
+ * socket interconnect.  node >= 0: the pages come from that node; node == -2: interleaved over all nodes
+ * (for boxes that do not tell which node a GPU hangs on); anything else: the default policy. */
+static long set_mempolicy_raw(int mode, const unsigned long *mask, unsigned long maxnode)
+{
+#ifdef SYS_set_mempolicy
+    return syscall(SYS_set_mempolicy, mode, mask, maxnode);
+#else
+    (void)mode; (void)mask; (void)maxnode;
+    return -1;
+#endif
+}
+
+static int numa_node_count()
+{
+    int n = 0;
+    for (int k = 0; k < 64; ++k) {
+        char path[64];
+        snprintf(path, sizeof path, "/sys/devices/system/node/node%d", k);
+        if (access(path, F_OK) == 0)
+            n = k + 1;
+    }
+    return n;
+}
+
+static int numa_node_of_device(int device)
+{
+    char bus[32] = {0}, path[128];
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    for (char *q = bus; *q; ++q)
+        *q = (char)tolower((unsigned char)*q);
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    if (!f)
+        return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1)
+        node = -1;
+    fclose(f);
+    return node;
+}
+
+static int host_alloc_policy(size_t bytes, void **out, int node)
 {
     if (!out) {
         fdtd_set_error("fdtd_host_alloc: NULL argument");
         return FDTD_E_ARG;
     }
+    const int nodes = numa_node_count();
+    bool policy_set = false;
+    if (nodes > 1 && nodes <= 64) {
+        unsigned long mask = 0;
+        int mode = 0;
+        if (node >= 0 && node < nodes) {
+            mask = 1ul << node;
+            mode = 1; /* MPOL_PREFERRED */
+        } else if (node == -2) {
+            mask = nodes == 64 ? ~0ul : (1ul << nodes) - 1;
+            mode = 3; /* MPOL_INTERLEAVE */
+        }
+        if (mask)
+            policy_set = set_mempolicy_raw(mode, &mask, 65) == 0;
+    }
     cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (policy_set)
+        set_mempolicy_raw(0 /* MPOL_DEFAULT */, nullptr, 0);
     if (e != cudaSuccess) {
         fdtd_set_error("cudaHostAlloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
         *out = nullptr;
         return e == cudaErrorMemoryAllocation ? FDTD_E_NOMEM : FDTD_E_CUDA;
     }
+    return FDTD_OK;
+}
+
+int fdtd_host_alloc(size_t bytes, void **out)
+{
+    return host_alloc_policy(bytes, out, -1);
+}
+
+int fdtd_host_alloc_near(int device, size_t bytes, void **out)
+{
+    /* FDTD_B200_HOST_NUMA: "near" (default: the node the GPU hangs on, if the box tells), "interleave", "off" */
+    const char *env = getenv("FDTD_B200_HOST_NUMA");
+    int node = -1;
+    if (env && !strcmp(env, "interleave"))
+        node = -2;
+    else if (!(env && !strcmp(env, "off")))
+        node = numa_node_of_device(device);
+    return host_alloc_policy(bytes, out, node);
+}
+
+int fdtd_host_numa_info(int device, int *nodes, int *node_of_device)
+{
+    if (nodes) *nodes = numa_node_count();
+    if (node_of_device) *node_of_device = numa_node_of_device(device);
     return FDTD_OK;
 }
 

@@ -144,7 +144,9 @@ struct fdtd_ctx {
     double *src_one_dev; /* single row for the operator-level fdtd_set_source */
 
     /* options */
-    long opt_kernel, opt_strip, opt_kchunk, opt_wx, opt_wy, opt_prefetch, opt_stages, opt_band, opt_l2promo, opt_cluster_x, opt_cluster_y;
+    long opt_kernel, opt_strip, opt_kchunk, opt_wx, opt_wy, opt_prefetch, opt_stages, opt_band, opt_l2promo, opt_cluster_x, opt_cluster_y, opt_persistent, opt_window;
+    unsigned *progress_dev; /* planes-completed counters of the persistent two-step kernel */
+    size_t progress_elems;
     long opt_host_chunk, opt_host_pipeline; /* fdtd_run_hosted: planes per z-chunk (0 = automatic), 0/1 */
     cudaStream_t s_h2d;                     /* uploads of fdtd_run_hosted (created on first use) */
 

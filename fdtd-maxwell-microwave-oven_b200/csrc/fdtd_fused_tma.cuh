@@ -50,6 +50,11 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned
                  : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
 {
     asm volatile(

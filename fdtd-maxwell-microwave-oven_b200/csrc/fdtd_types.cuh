@@ -76,6 +76,13 @@ struct Span {
     int kchunk;           /* planes per block */
     int prefetch;         /* planes ahead to pull into L2 (0 = off) */
     int band;             /* two-step kernel: tiles are handed out column by column inside bands of this many tile rows */
+    /* persistent form of the two-step kernel (k_step2_tma_ws): tiles per row / column of the cavity, the
+     * planes-completed counters (one row of counters per round of tiles) and how many planes a block may
+     * run ahead of the slowest block of its round */
+    int tiles_x, tiles_y;
+    unsigned *progress;
+    int progress_stride;
+    int window;
 };
 
 /* non-blocking hint: bring the line holding p into L2 (no register, no scoreboard entry) */

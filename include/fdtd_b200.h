@@ -134,7 +134,11 @@ int fdtd_ctx_peer_connect(fdtd_ctx *ctx, const void *blobs /* nranks x FDTD_PEER
  *   "warps_y"  kernel 4: block = 32 x warps_y threads storing 28 x (2 warps_y - 3) sites (8, 12, 16);
  *   "strip", "warps_x", "warps_y" kernels 1-3: rows per thread (1..4) and block shape in warps (at most 8
  *              warps; 16 for kernel 3);  "prefetch" planes of L2 prefetch ahead of the sweep (kernel 2);
- *   "band", "l2promo"  measurement knobs of kernel 4 (tile numbering, TMA L2 promotion);
+ *   "band", "l2promo", "cluster_x", "cluster_y"  measurement knobs of kernel 4 (tile numbering, TMA L2
+ *              promotion, thread-block clusters of neighbouring tiles);
+ *   "persistent" 1 = kernel 4 as one cooperative launch of as many blocks as the GPU holds, a producer warp
+ *              per block and flow control between the blocks ("window" planes); reads each array ~once,
+ *              bit-identical, not faster than the chunked form on a B200; default 0;
  *   "host_chunk", "host_pipeline"  fdtd_run_hosted (below).
  * Read-only: "k0", "k1" (owned cell planes), "launches" (kernels launched by this library so far),
  *   "fallback" (1 after the automatic fallback), "fused_ok" (second state copy available on every slab),
@@ -212,6 +216,12 @@ int fdtd_propagate(fdtd_ctx *ctx, const fdtd_dump_sink *sink, size_t *steps_done
 /* Pinned host memory for the arrays passed to fdtd_upload / fdtd_download (plain malloc'ed
  * arrays work too, at pageable-copy speed). */
 int fdtd_host_alloc(size_t bytes, void **out);
+/* Same, with the pages taken from the NUMA node the GPU `device` hangs on (when the box tells:
+ * /sys/bus/pci/devices/<id>/numa_node) -- on a two-socket box every rank should stream its slab through
+ * memory of its own socket.  FDTD_B200_HOST_NUMA=interleave spreads the pages over all nodes instead,
+ * =off keeps the default policy.  fdtd_host_numa_info reports what the box tells. */
+int fdtd_host_alloc_near(int device, size_t bytes, void **out);
+int fdtd_host_numa_info(int device, int *nodes, int *node_of_device);
 int fdtd_host_free(void *ptr);
 
 /* ---- all slabs of a cavity from ONE host thread ------------------------------------------------

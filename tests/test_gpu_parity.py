@@ -50,7 +50,11 @@ VARIANTS = [dict(kernel=0),
             dict(kernel=4),
             dict(kernel=4, kchunk=4, warps_y=8, stages=2),
             dict(kernel=4, kchunk=5, warps_y=16, stages=3),
-            dict(kernel=4, kchunk=1000, warps_y=12, stages=4)]
+            dict(kernel=4, kchunk=1000, warps_y=12, stages=4),
+            # persistent, warp-specialised cooperative form with flow control between the blocks of a round
+            dict(kernel=4, persistent=1, window=1),
+            dict(kernel=4, persistent=1, window=8, warps_y=16, stages=2),
+            dict(kernel=4, persistent=1, window=2, stages=5)]
 GRIDS = [(0.037, 0.029, 0.023), (0.013, 0.011, 0.009), (0.05, 0.04, 0.03), (0.065, 0.033, 0.012),
          (0.034, 0.066, 0.007),
          # I a multiple of the tile width: the last block in x holds the single column i = I

@@ -65,9 +65,12 @@ if args.small:
     variants.append(dict(kernel=1, strip=2, kchunk=8, warps_x=2, warps_y=2))
 if args.step2:
     variants = [dict(kernel=0), dict(kernel=3, strip=1, kchunk=32, stages=4, warps_x=1, warps_y=8)]
-    for kchunk, (cx, cy) in itertools.product((32, 64, 128), [(1, 1), (1, 2), (1, 4), (2, 2), (2, 4), (1, 8), (4, 2), (2, 1), (4, 1)]):
-        variants.append(dict(kernel=4, warps_y=8, stages=3, kchunk=kchunk, cluster_x=1, cluster_y=1))
-        variants[-1].update(cluster_x=cx, cluster_y=cy)
+    variants.append(dict(kernel=4, warps_y=8, stages=3, kchunk=32, persistent=0))
+    for wy, stages, window in itertools.product((8, 16), (3, 4, 5), (2, 4, 8, 32)):
+        if wy == 16 and stages == 5:
+            continue
+        variants.append(dict(kernel=4, warps_y=wy, stages=stages, kchunk=32, persistent=1, window=window))
+    variants.append(dict(kernel=4, warps_y=8, stages=3, kchunk=32, persistent=0))
 if args.only is not None:
     variants = [v for v in variants if v["kernel"] == args.only or v["kernel"] == 0]
 
