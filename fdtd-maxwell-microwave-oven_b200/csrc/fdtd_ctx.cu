@@ -279,8 +279,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
 
-int encode_maps(fdtd_ctx *c, int bx, int by, bool wide = false)
+int ring_slots(const fdtd_ctx *c) { return c->g.planes + 2 + kRollGap; }
+
+/* mode 0: planes 0 .. nk+1;  1 ("wide"): planes -1 .. nk+2;  2: the whole ring of slots (current set only) */
+int encode_maps(fdtd_ctx *c, int bx, int by, int mode = 0)
 {
+    const bool wide = mode >= 1;
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void *fn = nullptr;
@@ -293,7 +297,7 @@ int encode_maps(fdtd_ctx *c, int bx, int by, bool wide = false)
         encode = (EncodeTiledFn)fn;
     }
     double *sets[2] = {c->base, c->base2};
-    const bool same_shape = c->tma_bx == bx && c->tma_by == by && c->tma_promo == c->opt_l2promo && c->tma_wide == wide;
+    const bool same_shape = c->tma_bx == bx && c->tma_by == by && c->tma_promo == c->opt_l2promo && c->tma_mode == mode;
     if (same_shape && c->tma_base[0] == sets[0] && c->tma_base[1] == sets[1])
         return FDTD_OK;
     if (same_shape && c->tma_base[0] == sets[1] && c->tma_base[1] == sets[0]) {
@@ -302,7 +306,8 @@ int encode_maps(fdtd_ctx *c, int bx, int by, bool wide = false)
         return FDTD_OK;
     }
     /* wide: the tensor starts at the spare plane below plane 0, so local plane kl is z = kl + 1 */
-    const cuuint64_t dims[3] = {(cuuint64_t)c->g.P, (cuuint64_t)c->g.R, (cuuint64_t)(c->g.planes + (wide ? 2 : 0))};
+    const cuuint64_t dims[3] = {(cuuint64_t)c->g.P, (cuuint64_t)c->g.R,
+                                (cuuint64_t)(mode == 2 ? ring_slots(c) : c->g.planes + (wide ? 2 : 0))};
     const size_t shift = wide ? (size_t)c->g.PR : 0;
     const cuuint64_t strides[2] = {(cuuint64_t)c->g.P * 8, (cuuint64_t)c->g.PR * 8};
     const cuuint32_t box[3] = {(cuuint32_t)(bx + 4), (cuuint32_t)(by + 2), 1};
@@ -312,7 +317,7 @@ int encode_maps(fdtd_ctx *c, int bx, int by, bool wide = false)
                                          : c->opt_l2promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
                                                                : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     for (int set = 0; set < 2; ++set)
-        for (int a = 0; a < 6; ++a) {
+        for (int a = 0; a < 6 && sets[set]; ++a) {
             CUresult r = encode(&c->tma_maps[set].m[a], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
                                 sets[set] + (size_t)a * c->array_elems - shift, dims, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
@@ -325,7 +330,7 @@ int encode_maps(fdtd_ctx *c, int bx, int by, bool wide = false)
     c->tma_bx = bx;
     c->tma_by = by;
     c->tma_promo = (int)c->opt_l2promo;
-    c->tma_wide = wide;
+    c->tma_mode = mode;
     c->tma_base[0] = sets[0];
     c->tma_base[1] = sets[1];
     return FDTD_OK;
@@ -412,7 +417,7 @@ template <int WY>
 int launch_step2_t(fdtd_ctx *c, const Src &s1, const Src &s2, int kl_begin, int kl_end, cudaStream_t st)
 {
     constexpr int BYE = 2 * WY;
-    FDTD_TRY(encode_maps(c, kS2BoxW - 4, BYE - 1, true));
+    FDTD_TRY(encode_maps(c, kS2BoxW - 4, BYE - 1, c->rolling ? 2 : 1));
     /* as many stages as asked for, as far as the shared memory of one SM goes (at least two) */
     const size_t stage_bytes = (size_t)6 * tma_box_doubles(kS2BoxW - 4, BYE - 1) * sizeof(double);
     const int stages = (int)std::max(2L, std::min(c->opt_stages, (long)(200 * 1024 / stage_bytes)));
@@ -431,6 +436,25 @@ int launch_step2_t(fdtd_ctx *c, const Src &s1, const Src &s2, int kl_begin, int 
     dim3 grid((c->g.I + 1 + kS2TileX - 1) / kS2TileX, (c->g.J + 1 + BYE - 4) / (BYE - 3),
               (kl_end - kl_begin + sp.kchunk - 1) / sp.kchunk);
     Src2 src{s1, s2};
+    if (c->rolling) {
+        /* In place on the ring: plane k of the new state goes D slots below where plane k of the old one
+         * sits.  A chunk only ever overwrites slots whose planes the chunks before it have finished with
+         * (D >= planes per chunk + its run-in), so the chunks run one after another, bottom to top. */
+        const int Z = ring_slots(c);
+        const int kc = (int)std::min((long)sp.kchunk, (long)kRollGap - 4), D = kc + 4;
+        sp.kchunk = kc;
+        sp.zmod = Z;
+        sp.zrot_in = c->roll_rot;
+        sp.zrot_out = ((c->roll_rot - D) % Z + Z) % Z;
+        grid.z = 1;
+        for (int a = kl_begin; a < kl_end; a += kc) {
+            sp.kl_begin = a;
+            sp.kl_end = std::min(a + kc, kl_end);
+            k_step2_tma<WY><<<grid, block, smem, st>>>(c->g, c->tma_maps[0], c->f, c->ch, c->ce, src, sp, stages);
+            ++c->launches;
+        }
+        return FDTD_OK;
+    }
     const unsigned cx = (unsigned)c->opt_cluster_x, cy = (unsigned)c->opt_cluster_y;
     if (cx * cy > 8) {
         fdtd_set_error("two-step kernel: cluster_x (%u) * cluster_y (%u) must be <= 8", cx, cy);
@@ -525,7 +549,7 @@ int launch_step2(fdtd_ctx *c, const Src &s1, const Src &s2, int kl_begin, int kl
     if (kl_end <= kl_begin)
         return FDTD_OK;
     int rc;
-    if (c->opt_persistent)
+    if (c->opt_persistent && !c->rolling)
         rc = c->opt_wy > 8 ? launch_step2_ws_t<15>(c, s1, s2, kl_begin, kl_end, st)
                            : launch_step2_ws_t<7>(c, s1, s2, kl_begin, kl_end, st);
     else if (c->opt_wy >= 16)
@@ -544,6 +568,77 @@ void launch_set_source(const fdtd_ctx *c, const double *row_dev, cudaStream_t st
     dim3 grid((s.i1 - s.i0 + 31) / 32, (s.j1 - s.j0 + 7) / 8);
     k_set_source<<<grid, block, 0, st>>>(c->g, c->f, s);
     ++c->launches;
+}
+
+/* ---- the rolling window (in-place two-step sweeps) ----------------------------------------------- */
+
+static int roll_shift(const fdtd_ctx *c)
+{
+    return (int)std::min(std::max(c->opt_kchunk, 2L), (long)kRollGap - 4) + 4;
+}
+
+/* after a sweep: the state sits roll_shift() slots lower in every ring of the run (mine and, in
+ * lockstep, my neighbours') */
+static void roll_advance(fdtd_ctx *c)
+{
+    const int D = roll_shift(c), Z = ring_slots(c);
+    c->roll_rot = ((c->roll_rot - D) % Z + Z) % Z;
+    if (c->roll_peer_z_lo)
+        c->roll_peer_rot_lo = ((c->roll_peer_rot_lo - D) % c->roll_peer_z_lo + c->roll_peer_z_lo) % c->roll_peer_z_lo;
+    if (c->roll_peer_z_hi)
+        c->roll_peer_rot_hi = ((c->roll_peer_rot_hi - D) % c->roll_peer_z_hi + c->roll_peer_z_hi) % c->roll_peer_z_hi;
+}
+
+/* Rotate every ring back so that local plane -1 is in slot 0 again -- the layout everything outside
+ * the stepping loop expects.  Each slot moves once (cycle by cycle, one spare plane). */
+int roll_canonicalise(fdtd_ctx *c)
+{
+    if (!c->rolling || c->roll_rot == 0)
+        return FDTD_OK;
+    FDTD_TRY(wait_halos(c)); /* halo planes still arriving are part of the rings */
+    const int Z = ring_slots(c), r = c->roll_rot;
+    const size_t PR = (size_t)c->g.PR, bytes = PR * sizeof(double);
+    if (!c->roll_tmp)
+        CUDA_TRY(cudaMalloc((void **)&c->roll_tmp, bytes));
+    int g = Z, t = r;
+    while (t) {
+        const int u = g % t;
+        g = t;
+        t = u;
+    }
+    for (int a = 0; a < 6; ++a) {
+        double *slot0 = field_ptr(c, a) - PR;
+        for (int c0 = 0; c0 < g; ++c0) {
+            CUDA_TRY(cudaMemcpyAsync(c->roll_tmp, slot0 + (size_t)c0 * PR, bytes, cudaMemcpyDeviceToDevice, c->s_main));
+            int j = c0;
+            for (;;) {
+                const int src = (j + r) % Z;
+                if (src == c0)
+                    break;
+                CUDA_TRY(cudaMemcpyAsync(slot0 + (size_t)j * PR, slot0 + (size_t)src * PR, bytes, cudaMemcpyDeviceToDevice,
+                                         c->s_main));
+                j = src;
+            }
+            CUDA_TRY(cudaMemcpyAsync(slot0 + (size_t)j * PR, c->roll_tmp, bytes, cudaMemcpyDeviceToDevice, c->s_main));
+        }
+    }
+    c->roll_rot = c->roll_peer_rot_lo = c->roll_peer_rot_hi = 0; /* every slab of the run does this at the same point */
+    if (c->nranks > 1 && c->transport != TR_NCCL) {
+        /* a neighbour that pushes into (or pulls from) this slab must find the canonical layout: mark the
+         * point for the event transport; the flag transport orders through its acknowledgements */
+        CUDA_TRY(cudaEventRecord(c->ev_bnd, c->s_main));
+    }
+    return FDTD_OK;
+}
+
+static void announce_rolling(fdtd_ctx *c)
+{
+    if (!c->roll_announced && c->rank == 0 && !c->opt_rolling)
+        fprintf(stderr, "[fdtd_b200] a second copy of the state (%.1f GB per slab) does not fit in HBM on every slab: the "
+                        "two-step kernel works in place on a rolling window of plane slots (slower by its chunk-by-chunk "
+                        "launches, same results)\n", 6e-9 * (double)c->array_elems * sizeof(double));
+    c->roll_announced = true;
+    c->rolling = true;
 }
 
 /* A time step is made of segments -- one for the fused kernels (H and E in one sweep), two for the
@@ -566,7 +661,14 @@ int seg_launch(fdtd_ctx *c, const Src &s, Segment seg, const Src *second)
     if (seg == SEG_STEP2) {
         /* two steps in one sweep: reads c->f (with two halo planes each way), writes c->f2, swap.
          * The two planes at either end travel: they go first. */
-        if (!multi) {
+        if (c->rolling) {
+            /* in place on the ring, chunk after chunk from the bottom: nothing to reorder, the planes
+             * that travel up are final only at the end of the sweep */
+            FDTD_TRY(launch_step2(c, s, *second, 1, h_end, c->s_main));
+            if (multi)
+                CUDA_TRY(cudaEventRecord(c->ev_bnd, c->s_main));
+            roll_advance(c);
+        } else if (!multi) {
             FDTD_TRY(launch_step2(c, s, *second, 1, h_end, c->s_main));
         } else if (nk < 6) {
             FDTD_TRY(launch_step2(c, s, *second, 1, h_end, c->s_main));
@@ -588,7 +690,8 @@ int seg_launch(fdtd_ctx *c, const Src &s, Segment seg, const Src *second)
             CUDA_TRY(cudaEventRecord(c->ev_bnd, c->s_main));
             FDTD_TRY(launch_step2(c, s, *second, lo, hi, c->s_main));
         }
-        swap_buffers(c);
+        if (!c->rolling)
+            swap_buffers(c);
         c->e_halo_valid = c->h_halo_valid = c->low_e_halo_valid = c->wide_halo_valid = true; /* after the exchange */
     } else if (seg == SEG_FUSED) {
         /* reads c->f, writes c->f2, then the two swap */
@@ -742,8 +845,18 @@ int settle_kernel(fdtd_ctx *c)
 {
     if (c->opt_kernel < 2)
         return FDTD_OK;
+    if (c->opt_kernel == 4 && c->opt_rolling && step2_usable(c)) {
+        announce_rolling(c);
+        return FDTD_OK;
+    }
+    c->rolling = false;
     if (c->nranks == 1) {
         const int rc = ensure_pong(c);
+        if (rc == FDTD_E_NOMEM && c->opt_kernel == 4 && step2_usable(c)) {
+            cudaGetLastError();
+            announce_rolling(c);
+            return FDTD_OK;
+        }
         if (rc == FDTD_E_NOMEM && c->kernel_auto) {
             fall_back_to_split(c);
             return FDTD_OK;
@@ -757,6 +870,10 @@ int settle_kernel(fdtd_ctx *c)
     }
     if (c->fused_ok)
         return ensure_pong(c); /* already there */
+    if (c->opt_kernel == 4 && step2_usable(c)) { /* every rank sees the same fused_ok: the same decision */
+        announce_rolling(c);
+        return FDTD_OK;
+    }
     if (c->kernel_auto) {
         fall_back_to_split(c);
         return FDTD_OK;
@@ -823,6 +940,19 @@ int run_impl(fdtd_ctx *c, size_t steps, double *time_counter, float *total_ms, f
                 ++s;
                 continue;
             }
+            if (c->rolling) {
+                /* no second buffer set: the odd step runs with the in-place split kernels on the canonical layout */
+                FDTD_TRY(roll_canonicalise(c));
+                const long keep[5] = {c->opt_kernel, c->opt_strip, c->opt_kchunk, c->opt_wx, c->opt_wy};
+                c->opt_kernel = 1; c->opt_strip = 2; c->opt_kchunk = 8; c->opt_wx = 2; c->opt_wy = 2;
+                int rc1 = refresh_halos_many(&c, 1, false);
+                if (rc1 == FDTD_OK)
+                    rc1 = ev ? queue_step(c, src, evs[3 * gs], evs[3 * gs + 1], evs[3 * gs + 2])
+                             : queue_step(c, src, nullptr, nullptr, nullptr);
+                c->opt_kernel = keep[0]; c->opt_strip = keep[1]; c->opt_kchunk = keep[2]; c->opt_wx = keep[3]; c->opt_wy = keep[4];
+                FDTD_TRY(rc1);
+                continue;
+            }
             if (c->opt_kernel == 4)
                 FDTD_TRY(refresh_halos_many(&c, 1, true)); /* a single step after pairs, or slabs too thin for pairs */
             if (ev)
@@ -834,6 +964,7 @@ int run_impl(fdtd_ctx *c, size_t steps, double *time_counter, float *total_ms, f
         done += chunk;
     }
     *time_counter = t;
+    FDTD_TRY(roll_canonicalise(c)); /* (rolling form only) everything else expects the canonical layout */
     if (timed) {
         CUDA_TRY(cudaEventRecord(ev_end, c->s_main));
         if (c->nranks > 1)
@@ -918,7 +1049,7 @@ int create_impl(const fdtd_params *p, int device, int rank, int nranks, fdtd_ctx
     /* every array has one spare plane below local plane 0 and one above plane nk + 1: the second halo
      * plane of the two-steps-per-sweep kernel (local planes -1 and nk + 2).  Everything else addresses
      * planes 0 .. nk + 1 and never sees them. */
-    c->array_elems = (size_t)g.PR * (size_t)(g.planes + 2);
+    c->array_elems = (size_t)g.PR * (size_t)(g.planes + 2 + kRollGap);
     /* launch-shape limits: the per-cell kernels put one plane per blockIdx.z, and the fused kernels
      * index inside a plane with 32-bit offsets */
     if (g.planes > 65535 || g.PR >= (1LL << 31) - 4 * (long long)g.P) {
@@ -1053,6 +1184,7 @@ int fdtd_ctx_destroy(fdtd_ctx *c)
     if (c->src_host) cudaFreeHost(c->src_host);
     if (c->agg_dev) cudaFree(c->agg_dev);
     if (c->progress_dev) cudaFree(c->progress_dev);
+    if (c->roll_tmp) cudaFree(c->roll_tmp);
     cudaEvent_t evs[] = {c->ev_bnd, c->ev_sent, c->ev_hhalo, c->ev_ehalo, c->ev_src};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
@@ -1099,6 +1231,7 @@ int fdtd_ctx_set_option(fdtd_ctx *c, const char *key, long value)
     else if (!strcmp(key, "band") && value >= 1 && value <= 1024) c->opt_band = value;
     else if (!strcmp(key, "l2promo") && value >= 0 && value <= 3) c->opt_l2promo = value;
     else if (!strcmp(key, "persistent") && value >= 0 && value <= 1) c->opt_persistent = value;
+    else if (!strcmp(key, "rolling") && value >= 0 && value <= 1) c->opt_rolling = value;
     else if (!strcmp(key, "window") && value >= 1 && value <= 64) c->opt_window = value;
     else if (!strcmp(key, "cluster_x") && value >= 1 && value <= 8) c->opt_cluster_x = value;
     else if (!strcmp(key, "cluster_y") && value >= 1 && value <= 8) c->opt_cluster_y = value;
@@ -1128,6 +1261,7 @@ int fdtd_ctx_get_option(fdtd_ctx *c, const char *key, long *value)
     else if (!strcmp(key, "band")) *value = c->opt_band;
     else if (!strcmp(key, "l2promo")) *value = c->opt_l2promo;
     else if (!strcmp(key, "persistent")) *value = c->opt_persistent;
+    else if (!strcmp(key, "rolling")) *value = c->rolling ? 1 : c->opt_rolling;
     else if (!strcmp(key, "window")) *value = c->opt_window;
     else if (!strcmp(key, "cluster_x")) *value = c->opt_cluster_x;
     else if (!strcmp(key, "cluster_y")) *value = c->opt_cluster_y;

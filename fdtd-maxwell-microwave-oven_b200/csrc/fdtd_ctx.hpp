@@ -68,6 +68,11 @@ int nccl_bind();
 
 constexpr int kSrcRing = 512; /* source rows (steps) resident on the device at a time */
 
+/* Every array is allocated as a ring of nk + 4 + kRollGap plane slots: local planes -1 .. nk + 2 sit in
+ * slots 0 .. nk + 3, the gap behind them is what the in-place ("rolling") form of the two-step kernel
+ * shifts the state into, one chunk at a time (fdtd_ctx.cu, launch_step2_rolling). */
+constexpr int kRollGap = 40;
+
 /* How the halo planes travel between neighbouring slabs (fdtd_halo.cu):
  *   TR_NCCL   ncclSend / ncclRecv on the halo stream (one process per GPU, or a group);
  *   TR_EVENT  slabs of one fdtd_group: the receiver pulls the planes with a peer copy (copy engines, no
@@ -145,6 +150,12 @@ struct fdtd_ctx {
 
     /* options */
     long opt_kernel, opt_strip, opt_kchunk, opt_wx, opt_wy, opt_prefetch, opt_stages, opt_band, opt_l2promo, opt_cluster_x, opt_cluster_y, opt_persistent, opt_window;
+    long opt_rolling;       /* 1: the two-step kernel works in place on the rolling window even if a second set fits */
+    bool rolling;           /* ... it does (chosen, or the second set did not fit) */
+    bool roll_announced;
+    int roll_rot;           /* ring slot that holds local plane -1 right now (0 = canonical) */
+    int roll_peer_rot_lo, roll_peer_rot_hi, roll_peer_z_lo, roll_peer_z_hi; /* TR_FLAG: the neighbours' rings */
+    double *roll_tmp;       /* one plane, for rotating a ring back */
     unsigned *progress_dev; /* planes-completed counters of the persistent two-step kernel */
     size_t progress_elems;
     long opt_host_chunk, opt_host_pipeline; /* fdtd_run_hosted: planes per z-chunk (0 = automatic), 0/1 */
@@ -154,7 +165,7 @@ struct fdtd_ctx {
     TmaMaps tma_maps[2];
     double *tma_base[2];
     int tma_bx, tma_by, tma_promo;
-    bool tma_wide;
+    int tma_mode;       /* 0: planes 0 .. nk+1; 1: with the spare planes (-1 .. nk+2); 2: the whole ring of slots */
     const void *smem_optin[16]; /* kernels already opted in to large dynamic shared memory on this device */
     int n_smem_optin;
     mutable long launches; /* kernels of this library launched so far (reports) */
@@ -192,6 +203,8 @@ void launch_fused(fdtd_ctx *c, const fdtd::Src &s, int kl_begin, int kl_end, cud
 int launch_step2(fdtd_ctx *c, const fdtd::Src &s1, const fdtd::Src &s2, int kl_begin, int kl_end, cudaStream_t st);
 void swap_buffers(fdtd_ctx *c);
 int settle_kernel(fdtd_ctx *c);
+int roll_canonicalise(fdtd_ctx *c);
+int ring_slots(const fdtd_ctx *c);
 int ensure_pong(fdtd_ctx *c);
 void fall_back_to_split(fdtd_ctx *c);
 fdtd::Src make_src(const fdtd_ctx *c, const double *row);

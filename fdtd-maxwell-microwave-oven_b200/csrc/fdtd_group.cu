@@ -42,17 +42,27 @@ static int group_run(fdtd_ctx *const *cs, int n, size_t steps, double *time_coun
 {
     /* kernel choice must be the same on every slab: the halo plans differ */
     bool want_fused = cs[0]->opt_kernel >= 2;
-    if (want_fused) {
+    const bool can_roll = cs[0]->opt_kernel == 4 && step2_usable(cs[0]);
+    for (int r = 0; r < n; ++r)
+        cs[r]->rolling = can_roll && cs[0]->opt_rolling;
+    if (want_fused && !cs[0]->rolling) {
         bool nomem = false;
         for (int r = 0; r < n; ++r) {
             FDTD_TRY(use_device(cs[r]));
             const int rc = ensure_pong(cs[r]);
-            if (rc == FDTD_E_NOMEM && cs[r]->kernel_auto)
+            if (rc == FDTD_E_NOMEM && (cs[r]->kernel_auto || can_roll))
                 nomem = true;
             else if (rc != FDTD_OK)
                 return rc;
         }
-        if (nomem) {
+        if (nomem && can_roll) { /* in place on the rolling window instead of a second set */
+            if (!cs[0]->rolling)
+                fprintf(stderr, "[fdtd_b200] a second copy of the state does not fit in HBM on every slab: the two-step kernel "
+                                "works in place on a rolling window of plane slots\n");
+            for (int r = 0; r < n; ++r)
+                cs[r]->rolling = true;
+            cudaGetLastError();
+        } else if (nomem) {
             for (int r = 0; r < n; ++r) {
                 FDTD_TRY(use_device(cs[r]));
                 fall_back_to_split(cs[r]);
@@ -89,6 +99,33 @@ static int group_run(fdtd_ctx *const *cs, int n, size_t steps, double *time_coun
                 ++s;
                 continue;
             }
+            if (cs[0]->rolling) {
+                /* the odd step of a rolling run: in-place split kernels on the canonical layout */
+                long keep[5] = {cs[0]->opt_kernel, cs[0]->opt_strip, cs[0]->opt_kchunk, cs[0]->opt_wx, cs[0]->opt_wy};
+                int rc1 = FDTD_OK;
+                for (int r = 0; r < n && rc1 == FDTD_OK; ++r) {
+                    rc1 = use_device(cs[r]);
+                    if (rc1 == FDTD_OK)
+                        rc1 = roll_canonicalise(cs[r]);
+                    cs[r]->opt_kernel = 1; cs[r]->opt_strip = 2; cs[r]->opt_kchunk = 8; cs[r]->opt_wx = 2; cs[r]->opt_wy = 2;
+                }
+                if (rc1 == FDTD_OK)
+                    rc1 = refresh_halos_many(cs, n, false);
+                for (int g = 0; g < 2 && rc1 == FDTD_OK; ++g) {
+                    for (int r = 0; r < n && rc1 == FDTD_OK; ++r) {
+                        fdtd_ctx *c = cs[r];
+                        rc1 = seg_launch(c, make_src(c, c->src_dev + s * 2 * (size_t)c->src_n), split_plan[g]);
+                    }
+                    if (rc1 == FDTD_OK)
+                        rc1 = exchange_many(cs, n, seg_xchg(split_plan[g]), true);
+                }
+                for (int r = 0; r < n; ++r) {
+                    cs[r]->opt_kernel = keep[0]; cs[r]->opt_strip = keep[1]; cs[r]->opt_kchunk = keep[2];
+                    cs[r]->opt_wx = keep[3]; cs[r]->opt_wy = keep[4];
+                }
+                FDTD_TRY(rc1);
+                continue;
+            }
             if (pairs)
                 FDTD_TRY(refresh_halos_many(cs, n, true));
             for (int g = 0; g < nseg; ++g) {
@@ -104,6 +141,10 @@ static int group_run(fdtd_ctx *const *cs, int n, size_t steps, double *time_coun
         done += chunk;
     }
     *time_counter = t;
+    for (int r = 0; r < n; ++r) { /* (rolling form only) back to the canonical layout */
+        FDTD_TRY(use_device(cs[r]));
+        FDTD_TRY(roll_canonicalise(cs[r]));
+    }
     return FDTD_OK;
 }
 

@@ -169,10 +169,15 @@ static Lane down_lane(const Xchg &x, int nk_receiver)
     return l;
 }
 
-static double *plane_ptr(double *base, size_t array_elems, long long PR, int array, int plane)
+/* where local plane `plane` of array `array` is; Z > 0: the arrays are rings rotated by `rot` slots
+ * (rolling form of the two-step kernel), else plane -1 is simply the spare plane below plane 0 */
+static double *plane_ptr(double *base, size_t array_elems, long long PR, int array, int plane, int rot = 0, int Z = 0)
 {
-    return base + (size_t)array * array_elems + (long long)plane * PR; /* plane -1 is the spare plane */
+    const long long slot = Z ? (plane + 1 + rot) % Z : plane + 1;
+    return base + (size_t)array * array_elems + (slot - 1) * PR;
 }
+
+static int own_z(const fdtd_ctx *c) { return c->rolling ? ring_slots(c) : 0; }
 
 /* TR_NCCL: the sends and receives of one slab (inside the caller's NCCL group) */
 static int nccl_exchange(fdtd_ctx *c, cudaStream_t st, const Xchg &x)
@@ -185,27 +190,31 @@ static int nccl_exchange(fdtd_ctx *c, cudaStream_t st, const Xchg &x)
     const bool up = c->rank + 1 < c->nranks, lo = c->rank > 0;
     if (x.h) {
         const Lane l = up_lane(x, c->g.nk);
-        const size_t n = (size_t)PR * l.planes;
+        const size_t n = (size_t)PR; /* plane by plane: on a ring two planes need not be neighbours in memory */
         if (up)
             for (int i = 0; i < l.count; ++i)
-                NCCL_TRY(g_nccl.Send(plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.src), n, ncclDouble,
-                                     c->rank + 1, c->comm, st));
+                for (int q = 0; q < l.planes; ++q)
+                    NCCL_TRY(g_nccl.Send(plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.src + q, c->roll_rot, own_z(c)),
+                                         n, ncclDouble, c->rank + 1, c->comm, st));
         if (lo)
             for (int i = 0; i < l.count; ++i)
-                NCCL_TRY(g_nccl.Recv(plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.dst), n, ncclDouble,
-                                     c->rank - 1, c->comm, st));
+                for (int q = 0; q < l.planes; ++q)
+                    NCCL_TRY(g_nccl.Recv(plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.dst + q, c->roll_rot, own_z(c)),
+                                         n, ncclDouble, c->rank - 1, c->comm, st));
     }
     if (x.e) {
         const Lane l = down_lane(x, c->g.nk); /* as receiver: my own nk */
-        const size_t n = (size_t)PR * l.planes;
+        const size_t n = (size_t)PR;
         if (lo)
             for (int i = 0; i < l.count; ++i)
-                NCCL_TRY(g_nccl.Send(plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.src), n, ncclDouble,
-                                     c->rank - 1, c->comm, st));
+                for (int q = 0; q < l.planes; ++q)
+                    NCCL_TRY(g_nccl.Send(plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.src + q, c->roll_rot, own_z(c)),
+                                         n, ncclDouble, c->rank - 1, c->comm, st));
         if (up)
             for (int i = 0; i < l.count; ++i)
-                NCCL_TRY(g_nccl.Recv(plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.dst), n, ncclDouble,
-                                     c->rank + 1, c->comm, st));
+                for (int q = 0; q < l.planes; ++q)
+                    NCCL_TRY(g_nccl.Recv(plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.dst + q, c->roll_rot, own_z(c)),
+                                         n, ncclDouble, c->rank + 1, c->comm, st));
     }
     return FDTD_OK;
 }
@@ -218,19 +227,25 @@ static int event_pull(fdtd_ctx *c, cudaStream_t st, const Xchg &x)
         fdtd_ctx *s = c->nb_lo;
         CUDA_TRY(cudaStreamWaitEvent(st, s->ev_bnd, 0));
         const Lane l = up_lane(x, s->g.nk);
+        const bool ring = c->rolling || s->rolling; /* on a ring two planes need not be neighbours in memory */
         for (int i = 0; i < l.count; ++i)
-            CUDA_TRY(cudaMemcpyPeerAsync(plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.dst), c->device,
-                                         plane_ptr(s->base, s->array_elems, PR, l.arrays[i], l.src), s->device,
-                                         (size_t)PR * l.planes * sizeof(double), st));
+            for (int q = 0; q < l.planes; q += ring ? 1 : l.planes)
+                CUDA_TRY(cudaMemcpyPeerAsync(plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.dst + q, c->roll_rot, own_z(c)),
+                                             c->device,
+                                             plane_ptr(s->base, s->array_elems, PR, l.arrays[i], l.src + q, s->roll_rot, own_z(s)),
+                                             s->device, (size_t)PR * (ring ? 1 : l.planes) * sizeof(double), st));
     }
     if (x.e && c->nb_hi) {
         fdtd_ctx *s = c->nb_hi;
         CUDA_TRY(cudaStreamWaitEvent(st, s->ev_bnd, 0));
         const Lane l = down_lane(x, c->g.nk);
+        const bool ring = c->rolling || s->rolling; /* on a ring two planes need not be neighbours in memory */
         for (int i = 0; i < l.count; ++i)
-            CUDA_TRY(cudaMemcpyPeerAsync(plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.dst), c->device,
-                                         plane_ptr(s->base, s->array_elems, PR, l.arrays[i], l.src), s->device,
-                                         (size_t)PR * l.planes * sizeof(double), st));
+            for (int q = 0; q < l.planes; q += ring ? 1 : l.planes)
+                CUDA_TRY(cudaMemcpyPeerAsync(plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.dst + q, c->roll_rot, own_z(c)),
+                                             c->device,
+                                             plane_ptr(s->base, s->array_elems, PR, l.arrays[i], l.src + q, s->roll_rot, own_z(s)),
+                                             s->device, (size_t)PR * (ring ? 1 : l.planes) * sizeof(double), st));
     }
     return FDTD_OK;
 }
@@ -248,9 +263,11 @@ static int flag_push(fdtd_ctx *c, cudaStream_t st, const Xchg &x)
             FDTD_TRY(flag_wait(c, st, c->sig + SIG_UP_ACK, seq - 1));
             const Lane l = up_lane(x, c->g.nk);
             for (int i = 0; i < l.count; ++i)
-                CUDA_TRY(cudaMemcpyAsync(plane_ptr(c->peer_hi[c->flip], c->peer_elems_hi, PR, l.arrays[i], l.dst),
-                                         plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.src),
-                                         (size_t)PR * l.planes * sizeof(double), cudaMemcpyDefault, st));
+                for (int q = 0; q < l.planes; q += c->rolling ? 1 : l.planes)
+                    CUDA_TRY(cudaMemcpyAsync(plane_ptr(c->peer_hi[c->flip], c->peer_elems_hi, PR, l.arrays[i], l.dst + q,
+                                                       c->roll_peer_rot_hi, c->rolling ? c->roll_peer_z_hi : 0),
+                                             plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.src + q, c->roll_rot, own_z(c)),
+                                             (size_t)PR * (c->rolling ? 1 : l.planes) * sizeof(double), cudaMemcpyDefault, st));
             FDTD_TRY(flag_post(c, st, c->peer_sig_hi + SIG_UP_DATA, seq));
         }
     }
@@ -262,9 +279,11 @@ static int flag_push(fdtd_ctx *c, cudaStream_t st, const Xchg &x)
             FDTD_TRY(flag_wait(c, st, c->sig + SIG_DOWN_ACK, seq - 1));
             const Lane l = down_lane(x, c->peer_nk_lo);
             for (int i = 0; i < l.count; ++i)
-                CUDA_TRY(cudaMemcpyAsync(plane_ptr(c->peer_lo[c->flip], c->peer_elems_lo, PR, l.arrays[i], l.dst),
-                                         plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.src),
-                                         (size_t)PR * l.planes * sizeof(double), cudaMemcpyDefault, st));
+                for (int q = 0; q < l.planes; q += c->rolling ? 1 : l.planes)
+                    CUDA_TRY(cudaMemcpyAsync(plane_ptr(c->peer_lo[c->flip], c->peer_elems_lo, PR, l.arrays[i], l.dst + q,
+                                                       c->roll_peer_rot_lo, c->rolling ? c->roll_peer_z_lo : 0),
+                                             plane_ptr(c->base, c->array_elems, PR, l.arrays[i], l.src + q, c->roll_rot, own_z(c)),
+                                             (size_t)PR * (c->rolling ? 1 : l.planes) * sizeof(double), cudaMemcpyDefault, st));
             FDTD_TRY(flag_post(c, st, c->peer_sig_lo + SIG_DOWN_DATA, seq));
         }
     }
@@ -493,7 +512,7 @@ int fdtd_ctx_comm_init(fdtd_ctx *c, const void *id128)
     c->transport = TR_NCCL;
     /* agree on the fused kernels: minimum over the ranks of "I hold the second state copy" */
     int have = 0;
-    if (c->opt_kernel >= 2) {
+    if (c->opt_kernel >= 2 && !c->opt_rolling) {
         const int rc = ensure_pong(c);
         if (rc != FDTD_OK && rc != FDTD_E_NOMEM)
             return rc;
@@ -524,7 +543,7 @@ int fdtd_ctx_peer_export(fdtd_ctx *c, void *blob)
         return FDTD_E_STATE;
     }
     FDTD_TRY(use_device(c));
-    if (c->opt_kernel >= 2) {
+    if (c->opt_kernel >= 2 && !c->opt_rolling) {
         const int rc = ensure_pong(c);
         if (rc != FDTD_OK && rc != FDTD_E_NOMEM)
             return rc;
@@ -619,8 +638,8 @@ int fdtd_ctx_peer_connect(fdtd_ctx *c, const void *blobs)
     for (int r = 0; r < c->nranks; ++r) {
         memcpy(&all[r], (const char *)blobs + (size_t)r * FDTD_PEER_BLOB_BYTES, sizeof(PeerBlob));
         const PeerBlob &b = all[r];
-        if (b.magic != kBlobMagic || b.rank != r || b.nranks != c->nranks || b.array_elems / (size_t)(b.nk + 4) !=
-                                                                                 c->array_elems / (size_t)(c->g.nk + 4)) {
+        if (b.magic != kBlobMagic || b.rank != r || b.nranks != c->nranks || b.array_elems / (size_t)(b.nk + 4 + kRollGap) !=
+                                                                                 c->array_elems / (size_t)(c->g.nk + 4 + kRollGap)) {
             fdtd_set_error("fdtd_ctx_peer_connect: entry %d is not the export of rank %d of this cavity", r, r);
             return FDTD_E_ARG;
         }
@@ -630,11 +649,13 @@ int fdtd_ctx_peer_connect(fdtd_ctx *c, const void *blobs)
     if (c->rank > 0) {
         FDTD_TRY(map_peer(c, all[c->rank - 1], every_pong, c->peer_lo, &c->peer_sig_lo));
         c->peer_nk_lo = all[c->rank - 1].nk;
+        c->roll_peer_z_lo = all[c->rank - 1].nk + 4 + kRollGap;
         c->peer_elems_lo = (size_t)all[c->rank - 1].array_elems;
     }
     if (c->rank + 1 < c->nranks) {
         FDTD_TRY(map_peer(c, all[c->rank + 1], every_pong, c->peer_hi, &c->peer_sig_hi));
         c->peer_elems_hi = (size_t)all[c->rank + 1].array_elems;
+        c->roll_peer_z_hi = all[c->rank + 1].nk + 4 + kRollGap;
     }
     c->transport = TR_FLAG;
     c->flip = 0;

@@ -155,7 +155,7 @@ int fdtd_run_hosted(fdtd_ctx *c, const fdtd_fields *host, size_t steps, double *
     FDTD_TRY(use_device(c));
     FDTD_TRY(settle_kernel(c));
     const int kWave = 32; /* steps ramped in / out as a wavefront in a long run */
-    const bool pipelined = c->opt_host_pipeline && c->nranks == 1 && c->opt_kernel >= 2 && steps >= 1 &&
+    const bool pipelined = c->opt_host_pipeline && c->nranks == 1 && c->opt_kernel >= 2 && !c->rolling && steps >= 1 &&
                            steps <= (size_t)1 << 30;
     if (!pipelined) {
         FDTD_TRY(fdtd_upload_slab(c, host));

@@ -50,7 +50,8 @@ __device__ __forceinline__ void step2_sweep(const Geo &g, const TmaMaps &maps, c
                                             const double cE, const Src2 &src, const int stages, double *ring,
                                             double *xh, double *xe, unsigned long long *full, const int X0,
                                             const int Y0, const int kl0, const int kl1,
-                                            unsigned long long *empty = nullptr, unsigned *prog = nullptr)
+                                            unsigned long long *empty = nullptr, unsigned *prog = nullptr,
+                                            const int zmod = 0, const int zrot_in = 0, const int zrot_out = 0)
 {
     auto block_sync = [] {
         if (WS)
@@ -104,7 +105,8 @@ __device__ __forceinline__ void step2_sweep(const Geo &g, const TmaMaps &maps, c
         tma::mbar_expect_tx(bar, full_bytes);
 #pragma unroll
         for (int a = 0; a < 6; ++a)
-            tma::load_box(dst + a * box, &maps.m[a], X0 - 2, Y0 - 2, plane + 1, bar); /* the maps start at plane -1 */
+            tma::load_box(dst + a * box, &maps.m[a], X0 - 2, Y0 - 2, zmod ? (plane + 1 + zrot_in) % zmod : plane + 1,
+                          bar); /* the maps start at plane -1 */
     };
     if (!WS && leader)
         for (int n = 0; n < stages && n < nplanes; ++n)
@@ -132,6 +134,8 @@ __device__ __forceinline__ void step2_sweep(const Geo &g, const TmaMaps &maps, c
     int slot = 0;
     unsigned phase = 0;
     for (int k = kstart, n = 0; k <= kl1; ++k, ++n, pl += g.PR) {
+        if (zmod) /* rolling form: plane k - 1 goes to its slot of the ring (b points at slot 1) */
+            pl = (long long)((k + zrot_out) % zmod - 1) * g.PR;
         int slot1 = slot + 1;
         unsigned phase1 = phase;
         if (slot1 == stages) {
@@ -369,9 +373,11 @@ k_step2_tma(Geo g, const __grid_constant__ TmaMaps maps, Fld b, double cH, doubl
     /* every site of the extended tile strictly inside the walls: no predicate can be false */
     const bool interior = X0 - 2 >= 1 && X0 + 29 < g.I && Y0 - 2 >= 1 && Y0 - 2 + BYE - 1 < g.J;
     if (interior)
-        step2_sweep<WY, false, false>(g, maps, b, cH, cE, src, stages, ring, xh, xe, full, X0, Y0, kl0, kl1);
+        step2_sweep<WY, false, false>(g, maps, b, cH, cE, src, stages, ring, xh, xe, full, X0, Y0, kl0, kl1, nullptr,
+                                      nullptr, sp.zmod, sp.zrot_in, sp.zrot_out);
     else
-        step2_sweep<WY, true, false>(g, maps, b, cH, cE, src, stages, ring, xh, xe, full, X0, Y0, kl0, kl1);
+        step2_sweep<WY, true, false>(g, maps, b, cH, cE, src, stages, ring, xh, xe, full, X0, Y0, kl0, kl1, nullptr,
+                                     nullptr, sp.zmod, sp.zrot_in, sp.zrot_out);
 }
 
 /* The producer warp of the persistent form: lane 0 issues the six boxes of every plane of the sweep,

@@ -83,6 +83,10 @@ struct Span {
     unsigned *progress;
     int progress_stride;
     int window;
+    /* rolling (in-place) form of the two-step kernel: the arrays are rings of zmod plane slots; local plane
+     * kl is read from slot (kl + 1 + zrot_in) mod zmod and written to slot (kl + 1 + zrot_out) mod zmod.
+     * zmod == 0: the usual two buffer sets, plane kl at slot kl + 1 of each. */
+    int zmod, zrot_in, zrot_out;
 };
 
 /* non-blocking hint: bring the line holding p into L2 (no register, no scoreboard entry) */

@@ -35,6 +35,7 @@ def layouts(worlds=(2, 3, 4, 8)):
 
 
 VARIANTS = [dict(kernel=4, kchunk=4, warps_y=8, stages=2),
+            dict(kernel=4, rolling=1, kchunk=3),
             dict(kernel=3, strip=2, kchunk=4, warps_x=2, warps_y=2, stages=3),
             dict(kernel=2, strip=1, kchunk=32, warps_x=1, warps_y=4),
             dict(kernel=1, strip=2, kchunk=3, warps_x=2, warps_y=2),
@@ -150,7 +151,7 @@ def test_group_default_kernel_when_the_last_block_holds_one_column(F, oracle, di
 
 
 @pytest.mark.parametrize("nz", [6, 13])
-@pytest.mark.parametrize("kernel", [4, 3, 1])
+@pytest.mark.parametrize("kernel", [4, 3, 1, "rolling"])
 def test_many_short_runs_back_to_back_on_thin_slabs(F, oracle, kernel, nz):
     """Queue many short runs without synchronising in between, on slabs of one or two planes: every
     run must see the halos the previous one sent (the exchange of run n is still in flight when the
@@ -163,7 +164,11 @@ def test_many_short_runs_back_to_back_on_thin_slabs(F, oracle, kernel, nz):
     for world, devices, transport in layouts((4,)):
         f = oracle.alloc_fields(*dims, rng=np.random.default_rng(11))
         with F.Group(p, world, devices=devices, transport=transport) as g:
-            g.set_option("kernel", kernel)
+            if kernel == "rolling":
+                g.set_option("kernel", 4)
+                g.set_option("rolling", 1)
+            else:
+                g.set_option("kernel", kernel)
             g.upload(upper(f))
             t, total = 0.0, 0
             for n in range(20):

@@ -123,7 +123,10 @@ CASES = [((37, 28, 23), 1, 7, dict(kernel=1, strip=2, kchunk=8, warps_x=2, warps
          ((37, 28, 23), 1, 7, dict(kernel=4, kchunk=8)),
          ((70, 21, 8), 0, 6, dict(kernel=4, kchunk=3, warps_y=12, stages=2)),
          ((33, 40, 9), 1, 8, dict(kernel=4, kchunk=1000, warps_y=16)),
-         ((40, 33, 4), 1, 5, dict(kernel=4))]   # slabs too thin for the wide halos: single-step sweeps
+         ((40, 33, 4), 1, 5, dict(kernel=4)),   # slabs too thin for the wide halos: single-step sweeps
+         # in place on the rolling window (rings rotate in lockstep on every rank; uneven slabs have different rings)
+         ((37, 28, 23), 1, 7, dict(kernel=4, rolling=1, kchunk=5)),
+         ((33, 40, 9), 0, 6, dict(kernel=4, rolling=1))]
 
 
 if os.environ.get("FDTD_MULTI_QUICK") == "1":  # a short list for expensive many-GPU boxes

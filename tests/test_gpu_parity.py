@@ -54,7 +54,11 @@ VARIANTS = [dict(kernel=0),
             # persistent, warp-specialised cooperative form with flow control between the blocks of a round
             dict(kernel=4, persistent=1, window=1),
             dict(kernel=4, persistent=1, window=8, warps_y=16, stages=2),
-            dict(kernel=4, persistent=1, window=2, stages=5)]
+            dict(kernel=4, persistent=1, window=2, stages=5),
+            # in place on the rolling window of plane slots (what a context does when a second set does not fit)
+            dict(kernel=4, rolling=1),
+            dict(kernel=4, rolling=1, kchunk=4, warps_y=12, stages=2),
+            dict(kernel=4, rolling=1, kchunk=1000, warps_y=16)]
 GRIDS = [(0.037, 0.029, 0.023), (0.013, 0.011, 0.009), (0.05, 0.04, 0.03), (0.065, 0.033, 0.012),
          (0.034, 0.066, 0.007),
          # I a multiple of the tile width: the last block in x holds the single column i = I
