@@ -349,7 +349,8 @@ def main():
     peak, peak_src = peak_hbm()
     kopts = {k: ctx.get_option(k) for k in ("kernel", "strip", "kchunk", "warps_x", "warps_y", "stages")}
     kernel_id = kopts["kernel"]
-    cap = traffic_for(kopts)
+    rolling = bool(ctx.get_option("rolling"))
+    cap = None if rolling else traffic_for(kopts)    # no capture of the in-place (rolling window) form
     steps_per_launch = 1
     if kernel_id == 4:
         # ONE launch advances every cell by TWO time steps (an odd K ends with one single-step sweep)
@@ -484,7 +485,7 @@ def main():
                 "scaling": "strong" if args.nz_total is not None else "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic (hash-pattern fields in HBM, waveguide source on)",
                 "config": dict(workload_config(world, nz_total), kernel=kopts, transport=transport,
-                               fallback=bool(ctx.get_option("fallback"))),
+                               fallback=bool(ctx.get_option("fallback")), rolling_window=bool(ctx.get_option("rolling"))),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "selfcheck": selfcheck,
                 "gpu_launches": launches, "clocks": clocks.summary(), "hbm_bytes_per_gpu": ctx.info()["hbm_bytes"]}
         print(json.dumps(line), flush=True)

@@ -127,9 +127,13 @@ int fdtd_ctx_peer_connect(fdtd_ctx *ctx, const void *blobs /* nranks x FDTD_PEER
  *              3 = the same sweep with operands staged by TMA into a shared-memory ring;
  *              4 = TWO time steps per sweep over the TMA ring (default); an odd step and
  *                  slabs thinner than two planes take the single-step sweep of kernel 3.
- *              Left at its default the context falls back to kernel 1 -- with a line on stderr and
- *              "fallback" = 1 -- when the second copy of the state does not fit; a kernel chosen
- *              explicitly fails with FDTD_E_NOMEM instead.  On slabs, choose the kernel before wiring.
+ *              Kernels 2-4 keep the state twice in HBM.  When the second copy does not fit, kernel 4
+ *              works in place on a rolling window of plane slots instead ("rolling" reads 1; 1.04 x
+ *              the state, about two thirds of the speed) -- with a line on stderr.  Only
+ *              where that is impossible (kernels 2, 3; slabs thinner than two planes) a context left at
+ *              its defaults falls back to kernel 1 ("fallback" = 1) and a kernel chosen explicitly fails
+ *              with FDTD_E_NOMEM.  On slabs, choose the kernel before wiring.
+ *   "rolling"  1 = take the rolling-window form of kernel 4 even if a second copy would fit.
  *   "kchunk"   planes per block;  "stages" depth of the TMA ring (kernels 3, 4);
  *   "warps_y"  kernel 4: block = 32 x warps_y threads storing 28 x (2 warps_y - 3) sites (8, 12, 16);
  *   "strip", "warps_x", "warps_y" kernels 1-3: rows per thread (1..4) and block shape in warps (at most 8
