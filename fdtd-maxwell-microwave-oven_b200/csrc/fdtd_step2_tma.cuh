@@ -391,8 +391,6 @@ __device__ __forceinline__ void step2_produce(const Geo &g, const TmaMaps &maps,
                                               const int Y0, const int kl0, const int kl1, const unsigned *prog,
                                               const unsigned nblocks, const int window)
 {
-    if (threadIdx.x != 0)
-        return;
     constexpr int BYE = 2 * WY, W = kS2BoxW, HH = BYE + 1;
     const int box = tma_box_doubles(W - 4, HH - 2);
     const int stage_doubles = 6 * box;
@@ -400,27 +398,32 @@ __device__ __forceinline__ void step2_produce(const Geo &g, const TmaMaps &maps,
     const int kstart = max(kl0 - 2, g0);
     const int nplanes = kl1 - kstart + 2;
     const unsigned full_bytes = 6u * (unsigned)(W * HH) * 8u;
-    int slot = 0;
-    unsigned parity = 1; /* of the wait on `empty` for the current pass over the ring (first pass: none) */
-    for (int m = 0; m < nplanes; ++m) {
-        if (m >= stages)
-            tma::mbar_wait(empty + slot, parity);
-        const int idx = m - stages - window;
-        if (prog && idx >= 0) {
-            const volatile unsigned *gate = prog + idx;
-            while (*gate < nblocks)
-                __nanosleep(64);
-        }
-        double *dst = ring + (size_t)slot * stage_doubles;
-        tma::mbar_expect_tx(full + slot, full_bytes);
+    /* lane 0 does the work; the other lanes wait for it here, so that the warp reaches the block-wide
+     * barrier of the round loop as one (bar.sync is a per-warp instruction) */
+    if (threadIdx.x == 0) {
+        int slot = 0;
+        unsigned parity = 1; /* of the wait on `empty` for the current pass over the ring (first pass: none) */
+        for (int m = 0; m < nplanes; ++m) {
+            if (m >= stages)
+                tma::mbar_wait(empty + slot, parity);
+            const int idx = m - stages - window;
+            if (prog && idx >= 0) {
+                const volatile unsigned *gate = prog + idx;
+                while (*gate < nblocks)
+                    __nanosleep(64);
+            }
+            double *dst = ring + (size_t)slot * stage_doubles;
+            tma::mbar_expect_tx(full + slot, full_bytes);
 #pragma unroll
-        for (int a = 0; a < 6; ++a)
-            tma::load_box(dst + a * box, &maps.m[a], X0 - 2, Y0 - 2, kstart + m + 1, full + slot);
-        if (++slot == stages) {
-            slot = 0;
-            parity ^= 1u;
+            for (int a = 0; a < 6; ++a)
+                tma::load_box(dst + a * box, &maps.m[a], X0 - 2, Y0 - 2, kstart + m + 1, full + slot);
+            if (++slot == stages) {
+                slot = 0;
+                parity ^= 1u;
+            }
         }
     }
+    __syncwarp();
 }
 
 /* Persistent, cooperative, warp-specialised form: one block of WY compute warps + 1 producer warp per

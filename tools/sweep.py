@@ -65,10 +65,9 @@ if args.small:
     variants.append(dict(kernel=1, strip=2, kchunk=8, warps_x=2, warps_y=2))
 if args.step2:
     variants = [dict(kernel=0), dict(kernel=3, strip=1, kchunk=32, stages=4, warps_x=1, warps_y=8)]
-    variants.append(dict(kernel=4, warps_y=8, stages=3, kchunk=32, persistent=0))
-    for wy, stages, window in itertools.product((8, 16), (3, 4, 5), (2, 4, 8, 32)):
-        if wy == 16 and stages == 5:
-            continue
+    for wy, stages, kchunk in itertools.product((8, 16), (2, 3, 4), (24, 32, 64)):
+        variants.append(dict(kernel=4, warps_y=wy, stages=stages, kchunk=kchunk, persistent=0))
+    for wy, stages, window in itertools.product((8, 16), (3, 4), (2, 8)):
         variants.append(dict(kernel=4, warps_y=wy, stages=stages, kchunk=32, persistent=1, window=window))
     variants.append(dict(kernel=4, warps_y=8, stages=3, kchunk=32, persistent=0))
 if args.only is not None:
