@@ -1,8 +1,12 @@
 #!/bin/bash
-# 8-GPU validation (run under gpurun --gpus 8): world-8 slab tests, weak and strong scaling benches
+# 8-GPU session on ONE box (run under gpurun --gpus 8): same-box scaling table, weak and strong
 mkdir -p gpurun_out
-FDTD_MULTI_QUICK=1 timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -q -x -k "8-peer or 8-nccl" > gpurun_out/pytest_multi_8.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_multi_8.log
-export BENCH_TAG=n8_weak; tools/gpu.sh benchn 8 --steps 20 --warmup 5
-export BENCH_TAG=n8_weak_nccl; tools/gpu.sh benchn 8 --steps 20 --warmup 5 --transport nccl --no-e2e --no-selfcheck
-export BENCH_TAG=n8_strong2048; tools/gpu.sh benchn 8 --steps 40 --workload strong2048 --no-e2e
-export BENCH_TAG=n8_cube2048; tools/gpu.sh benchn 8 --steps 20 --workload cube2048 --no-e2e
+{ nvidia-smi topo -m; lscpu | grep -i "numa\|socket\|^cpu(s)\|model name"; free -g | head -2; } > gpurun_out/box8_topology.txt 2>&1
+if [ "$1" == "tests" ]; then
+  FDTD_MULTI_QUICK=1 timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -q -x -k "8-peer or 8-nccl" > gpurun_out/pytest_multi_8.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_multi_8.log
+fi
+export BENCH_TAG=scale_n1; tools/gpu.sh bench --steps 20 --warmup 5 --no-e2e --no-cpu
+for n in 2 4; do export BENCH_TAG=scale_n$n; tools/gpu.sh benchn $n --steps 20 --warmup 5 --no-e2e; done
+export BENCH_TAG=scale_n8; tools/gpu.sh benchn 8 --steps 20 --warmup 5
+export BENCH_TAG=strong2048_n4; tools/gpu.sh benchn 4 --steps 40 --workload strong2048 --no-e2e
+export BENCH_TAG=strong2048_n8; tools/gpu.sh benchn 8 --steps 40 --workload strong2048 --no-e2e
