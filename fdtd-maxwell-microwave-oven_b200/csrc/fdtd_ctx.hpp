@@ -219,6 +219,8 @@ int exchange_many(fdtd_ctx *const *cs, int n, const Xchg &x, bool on_comm);
 int wait_halos(fdtd_ctx *c);
 /* bring the halos the selected kernels need up to date (after uploads and operator-level calls) */
 int refresh_halos_many(fdtd_ctx *const *cs, int n, bool fused, bool wide = false);
+int halo_side_wait(fdtd_ctx *c, bool top, unsigned seq);
+int halo_side_push(fdtd_ctx *c, bool top, unsigned consumed, unsigned seq, double *src_base, int dst_parity);
 void halo_destroy(fdtd_ctx *c);
 int alloc_sig(fdtd_ctx *c);
 

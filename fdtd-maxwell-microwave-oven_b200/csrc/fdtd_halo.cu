@@ -290,6 +290,46 @@ static int flag_push(fdtd_ctx *c, cudaStream_t st, const Xchg &x)
     return FDTD_OK;
 }
 
+/* ---- one side of a slab at a time (the hosted wavefront over several slabs, fdtd_hosted.cu) ----------
+ * TR_FLAG only, everything on the compute stream.  `top`: the interface with the slab above (else below).
+ * Sequence numbers continue the lanes' own (n_xh for the upward lane, n_xe for the downward one). */
+
+/* the compute stream waits until the neighbour on that side has delivered its planes number `seq` */
+int halo_side_wait(fdtd_ctx *c, bool top, unsigned seq)
+{
+    return flag_wait(c, c->s_main, c->sig + (top ? SIG_DOWN_DATA : SIG_UP_DATA), seq);
+}
+
+/* tell that neighbour that its planes number `consumed` have been used, then send it my two boundary planes
+ * of the state in `src_base` (all six arrays) as number `seq`, into its buffer set `dst_parity` */
+int halo_side_push(fdtd_ctx *c, bool top, unsigned consumed, unsigned seq, double *src_base, int dst_parity)
+{
+    const long long PR = c->g.PR;
+    Xchg x{};
+    x.h = x.e = x.wide = true;
+    cudaStream_t st = c->s_main;
+    if (top) {
+        FDTD_TRY(flag_post(c, st, c->peer_sig_hi + SIG_DOWN_ACK, consumed));
+        FDTD_TRY(flag_wait(c, st, c->sig + SIG_UP_ACK, seq - 2));
+        const Lane l = up_lane(x, c->g.nk);
+        for (int i = 0; i < l.count; ++i)
+            CUDA_TRY(cudaMemcpyAsync(plane_ptr(c->peer_hi[dst_parity], c->peer_elems_hi, PR, l.arrays[i], l.dst),
+                                     plane_ptr(src_base, c->array_elems, PR, l.arrays[i], l.src),
+                                     (size_t)PR * l.planes * sizeof(double), cudaMemcpyDefault, st));
+        FDTD_TRY(flag_post(c, st, c->peer_sig_hi + SIG_UP_DATA, seq));
+    } else {
+        FDTD_TRY(flag_post(c, st, c->peer_sig_lo + SIG_UP_ACK, consumed));
+        FDTD_TRY(flag_wait(c, st, c->sig + SIG_DOWN_ACK, seq - 2));
+        const Lane l = down_lane(x, c->peer_nk_lo);
+        for (int i = 0; i < l.count; ++i)
+            CUDA_TRY(cudaMemcpyAsync(plane_ptr(c->peer_lo[dst_parity], c->peer_elems_lo, PR, l.arrays[i], l.dst),
+                                     plane_ptr(src_base, c->array_elems, PR, l.arrays[i], l.src),
+                                     (size_t)PR * l.planes * sizeof(double), cudaMemcpyDefault, st));
+        FDTD_TRY(flag_post(c, st, c->peer_sig_lo + SIG_DOWN_DATA, seq));
+    }
+    return FDTD_OK;
+}
+
 int wait_halos(fdtd_ctx *c)
 {
     if (c->nranks == 1)

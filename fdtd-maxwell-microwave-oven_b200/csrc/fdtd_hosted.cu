@@ -34,8 +34,9 @@ namespace fdtdi {
 struct Chunks {
     int planes;              /* local planes 1 .. planes are swept (nk + 1 on the last slab) */
     int size, count;
+    int last_extra = 0;      /* planes the last chunk takes on top of `size` (so that it is never a single plane) */
     int begin(int c) const { return 1 + c * size; }
-    int end(int c) const { return std::min(1 + (c + 1) * size, planes + 1); }
+    int end(int c) const { return c == count - 1 ? planes + 1 : std::min(1 + (c + 1) * size, planes + 1); }
 };
 
 static double *host_array(const fdtd_fields *h, int idx)
@@ -141,6 +142,129 @@ static int wavefront(fdtd_ctx *c, const fdtd_fields *host, const Chunks &ch, int
     return rc;
 }
 
+/* The same wavefront for a slab with neighbours (one process per GPU, peer-memory halos).  A sweep of the
+ * chunk next to an interface needs the neighbour's boundary planes of the previous sweep, so the slabs'
+ * wavefronts have to mesh: neighbouring slabs sweep their chunks in OPPOSITE directions (even ranks
+ * bottom-up, odd ranks top-down).  Then every interface is either the first thing both of its slabs
+ * touch in a wave or the last, the two sides reach it in the same wave, and what one side needs from
+ * the other is always one sweep older -- each slab streams upload, sweeps and download at its own PCIe
+ * rate, and the halo planes of sweep s travel right after the boundary chunk of sweep s.  Everything
+ * is queued on the compute stream; sequence flags order it against the neighbours (fdtd_halo.cu). */
+static int wavefront_slab(fdtd_ctx *c, const fdtd_fields *host, const Chunks &ch, int nsteps_in, const double *src_rows)
+{
+    const int M = ch.count;
+    const size_t row = 2 * (size_t)c->src_n;
+    const int S = (nsteps_in + 1) / 2; /* sweeps of two steps (the last one single when the count is odd) */
+    const bool up_first = (c->rank & 1) == 0;
+    const bool has_lo = c->rank > 0, has_hi = c->rank + 1 < c->nranks;
+    auto chunk_of = [&](int q) { return up_first ? q : M - 1 - q; };
+    const unsigned base_h = c->n_xh, base_e = c->n_xe; /* lane numbering so far; push p of a lane = base + 1 + p */
+    const int flip0 = c->flip;
+    struct Events {
+        std::vector<cudaEvent_t> v;
+        ~Events()
+        {
+            for (cudaEvent_t e : v)
+                if (e)
+                    cudaEventDestroy(e);
+        }
+    } ups, dones;
+    ups.v.assign(M, nullptr);
+    dones.v.assign(M, nullptr);
+    for (auto &e : ups.v)
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : dones.v)
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    FDTD_TRY(wait_halos(c)); /* nothing of earlier exchanges is still in flight */
+    CUDA_TRY(cudaEventRecord(ups.v[0], c->s_main));
+    CUDA_TRY(cudaStreamWaitEvent(c->s_h2d, ups.v[0], 0));
+    for (int q = 0; q < M; ++q) {
+        const int k = chunk_of(q);
+        for (int a = 0; a < 6; ++a)
+            FDTD_TRY(copy_planes(c, a, host_array(host, a), ch.begin(k), ch.end(k), true, c->s_h2d));
+        CUDA_TRY(cudaEventRecord(ups.v[q], c->s_h2d));
+    }
+    /* which interfaces does the chunk at order position q touch? */
+    auto touches_top = [&](int q) { return has_hi && chunk_of(q) == M - 1; };
+    auto touches_bottom = [&](int q) { return has_lo && chunk_of(q) == 0; };
+    auto push = [&](bool top, int p, double *src_base) { /* my boundary planes of X[p] */
+        const unsigned b = top ? base_h : base_e;          /* outgoing lane: upward at the top, downward at the bottom */
+        const unsigned bin = top ? base_e : base_h;        /* incoming lane of that side */
+        return halo_side_push(c, top, bin + (unsigned)p, b + 1 + (unsigned)p, src_base, (flip0 + p) & 1);
+    };
+    int parity = 0;
+    bool pushed0_top = false, pushed0_bottom = false;
+    for (int u = 1; u <= M - 1 + S; ++u) {
+        if (u <= M)
+            CUDA_TRY(cudaStreamWaitEvent(c->s_main, ups.v[std::min(u, M - 1)], 0));
+        /* the freshly uploaded boundary planes are the neighbours' halo of the initial state */
+        const int landed = std::min(u, M - 1);
+        for (int q = 0; q <= landed; ++q) {
+            if (touches_top(q) && !pushed0_top && q <= landed) {
+                if (parity != 0) { swap_buffers(c); parity = 0; }
+                FDTD_TRY(push(true, 0, c->base));
+                pushed0_top = true;
+            }
+            if (touches_bottom(q) && !pushed0_bottom && q <= landed) {
+                if (parity != 0) { swap_buffers(c); parity = 0; }
+                FDTD_TRY(push(false, 0, c->base));
+                pushed0_bottom = true;
+            }
+        }
+        for (int s = std::max(1, u - M + 1); s <= std::min(S, u); ++s) {
+            const int q = u - s, k = chunk_of(q);
+            if (((s - 1) & 1) != parity) { /* sweep s reads X[s-1] */
+                swap_buffers(c);
+                parity ^= 1;
+            }
+            /* the neighbours' boundary planes of X[s-1] */
+            if (touches_top(q))
+                FDTD_TRY(halo_side_wait(c, true, base_e + (unsigned)s));
+            if (touches_bottom(q))
+                FDTD_TRY(halo_side_wait(c, false, base_h + (unsigned)s));
+            if (2 * s <= nsteps_in) {
+                const int rc2 = launch_step2(c, make_src(c, src_rows + (size_t)(2 * s - 2) * row),
+                                             make_src(c, src_rows + (size_t)(2 * s - 1) * row), ch.begin(k), ch.end(k), c->s_main);
+                if (rc2 != FDTD_OK)
+                    return rc2;
+            } else {
+                launch_fused(c, make_src(c, src_rows + (size_t)(nsteps_in - 1) * row), ch.begin(k), ch.end(k), c->s_main);
+                if (c->launch_error != FDTD_OK) {
+                    const int rc2 = c->launch_error;
+                    c->launch_error = FDTD_OK;
+                    return rc2;
+                }
+            }
+            /* my boundary planes of X[s] (just written into the other set) for the neighbours' sweep s + 1 */
+            if (touches_top(q))
+                FDTD_TRY(push(true, s, c->base2));
+            if (touches_bottom(q))
+                FDTD_TRY(push(false, s, c->base2));
+            if (s == S) {
+                CUDA_TRY(cudaEventRecord(dones.v[q], c->s_main));
+                CUDA_TRY(cudaStreamWaitEvent(c->s_dump, dones.v[q], 0));
+                swap_buffers(c); /* copy_planes reads c->f */
+                int rc2 = FDTD_OK;
+                for (int a = 0; a < 6 && rc2 == FDTD_OK; ++a)
+                    rc2 = copy_planes(c, a, host_array(host, a), ch.begin(k), ch.end(k), false, c->s_dump);
+                swap_buffers(c);
+                FDTD_TRY(rc2);
+            }
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    if ((S & 1) != parity)
+        swap_buffers(c);
+    /* the lanes have seen one initial push and S more; what the neighbours sent last is the halo of X[S] */
+    c->n_xh = base_h + 1 + (unsigned)S;
+    c->n_xe = base_e + 1 + (unsigned)S;
+    CUDA_TRY(cudaEventRecord(c->ev_sent, c->s_main));
+    c->e_halo_valid = c->h_halo_valid = c->low_e_halo_valid = c->wide_halo_valid = true;
+    CUDA_TRY(cudaEventRecord(dones.v[0], c->s_dump));
+    CUDA_TRY(cudaStreamWaitEvent(c->s_main, dones.v[0], 0));
+    return FDTD_OK;
+}
+
 } /* namespace fdtdi */
 
 extern "C" {
@@ -157,6 +281,28 @@ int fdtd_run_hosted(fdtd_ctx *c, const fdtd_fields *host, size_t steps, double *
     const int kWave = 32; /* steps ramped in / out as a wavefront in a long run */
     const bool pipelined = c->opt_host_pipeline && c->nranks == 1 && c->opt_kernel >= 2 && !c->rolling && steps >= 1 &&
                            steps <= (size_t)1 << 30;
+    /* slabs: the meshed wavefront needs the two-step kernel's wide halos, peer-memory flags, a second buffer
+     * set and a run short enough to be one wavefront (the same decision on every rank) */
+    const bool meshed = c->opt_host_pipeline && c->nranks > 1 && c->transport == TR_FLAG && c->opt_kernel == 4 &&
+                        !c->rolling && step2_usable(c) && steps >= 1 && steps <= 2 * (size_t)kWave;
+    if (meshed) {
+        if (!c->s_h2d)
+            CUDA_TRY(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+        Chunks ch;
+        ch.planes = c->g.nk + c->g.top;
+        ch.size = c->opt_host_chunk > 0 ? (int)c->opt_host_chunk : std::max(8, (ch.planes + 255) / 256);
+        ch.size = std::max(ch.size, 2);
+        ch.count = (ch.planes + ch.size - 1) / ch.size;
+        if (ch.count >= 2 && ch.planes - (ch.count - 1) * ch.size < 2) /* the last chunk carries two boundary planes */
+            ch.count -= 1, ch.last_extra = ch.planes - ch.count * ch.size;
+        double t = *time_counter;
+        FDTD_TRY(stage_source_rows(c, steps, &t));
+        FDTD_TRY(wavefront_slab(c, host, ch, (int)steps, c->src_dev));
+        CUDA_TRY(cudaStreamSynchronize(c->s_dump));
+        CUDA_TRY(cudaStreamSynchronize(c->s_main));
+        *time_counter = t;
+        return FDTD_OK;
+    }
     if (!pipelined) {
         FDTD_TRY(fdtd_upload_slab(c, host));
         FDTD_TRY(run_impl(c, steps, time_counter, nullptr, nullptr, nullptr));

@@ -97,6 +97,32 @@ def _worker(rank, world, port, transport, cases, ret):
                     if not np.array_equal(ctx.aggregate(v).view(np.uint64), want.view(np.uint64)):
                         bad.append((case, "aggregate", v))
                 sums = ctx.checksum()
+                # fdtd_run_hosted on slabs: host arrays of my planes in, 5 steps, host arrays out.  With peer memory
+                # and the two-step kernel the slabs' wavefronts mesh (neighbours sweep in opposite directions);
+                # everything else takes upload + run + download.
+                ref = {k.lower(): v.copy() for k, v in init.items()}
+                o.run(q, ref, 5)
+                top = 1 if rank == world - 1 else 0
+                k0, k1 = ctx.k0, ctx.k1
+                for chunk in (2, 3):
+                    ctx.set_option("host_chunk", chunk)
+                    mine = {}
+                    for name, arr in init.items():
+                        hi = k1 + top if name in ("Ex", "Ey", "Hz") else k1
+                        mine[name] = arr[k0:hi].copy()      # (a leading-axis slice is a view: the call works in place)
+                    t_h = ctx.run_hosted(mine, 5, 0.0)
+                    for name, arr in mine.items():
+                        hi = k1 + top if name in ("Ex", "Ey", "Hz") else k1
+                        if not np.array_equal(arr.view(np.uint64), ref[name.lower()][k0:hi].view(np.uint64)):
+                            bad.append((case, f"hosted chunk {chunk}", name))
+                    # the device state and its halos are current too: one more step from there
+                    t_h = ctx.run(1, t_h)
+                    ref1 = {k: v.copy() for k, v in ref.items()}
+                    o.run(q, ref1, 1, 5 * DT)
+                    got = ctx.download({k: np.zeros_like(v) for k, v in init.items()})
+                    for name in ("Ez", "Hx", "Hy"):
+                        if not np.array_equal(got[name][k0:k1].view(np.uint64), ref1[name.lower()][k0:k1].view(np.uint64)):
+                            bad.append((case, f"hosted chunk {chunk} + run", name))
                 dist.barrier()   # nobody unmaps a neighbour's memory while it may still be written
             allsums = [None] * world
             dist.all_gather_object(allsums, sums)
