@@ -182,7 +182,9 @@ int fdtd_sync(fdtd_ctx *ctx);
  * reference's dense layout (as for fdtd_upload_slab) and is advanced in place by `steps` passes.
  * On a single-slab context with the fused kernels the upload, the stepping and the download run as one
  * wavefront over z-chunks (chunk c of step s only needs chunks c-1, c, c+1 of step s-1), so the two
- * PCIe directions and the kernels overlap; results are bit-identical to fdtd_upload_slab + fdtd_run +
+ * PCIe directions and the kernels overlap.  Slabs wired through peer memory do the same for runs of up
+ * to 64 steps, with neighbouring slabs sweeping in opposite directions so that their wavefronts mesh
+ * (call it on every rank).  Results are bit-identical to fdtd_upload_slab + fdtd_run +
  * fdtd_download_slab, which is also what other contexts do.  Use pinned arrays (fdtd_host_alloc).
  * Options: "host_chunk" planes per z-chunk (0 = automatic), "host_pipeline" 0 = always in sequence.
  * Blocks until the host arrays hold the result. */
