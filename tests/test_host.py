@@ -157,3 +157,27 @@ def test_host_helpers_match_oracle_on_random_parameters(F, oracle, tmp_path):
         plan = F.source_plan(a)
         assert (plan.i0, plan.i1, plan.j0, plan.j1) == oracle.source_bounds(b), nums
         assert plan.z_te == oracle.source_zte(b) or (np.isnan(plan.z_te) and np.isnan(oracle.source_zte(b))), nums
+
+
+def test_constants_of_the_header_match_the_glue(F):
+    """FDTD_PEER_BLOB_BYTES in include/fdtd_b200.h is what the ctypes glue allocates; the NUMA query works
+    without a device (one node or none reported for the GPU is fine: the allocation then uses the default policy)."""
+    import re
+    from conftest import ROOT
+    text = open(os.path.join(ROOT, "include", "fdtd_b200.h")).read()
+    assert int(re.search(r"#define FDTD_PEER_BLOB_BYTES (\d+)", text).group(1)) == F.PEER_BLOB_BYTES
+    info = F.host_numa_info(0)
+    assert info["nodes"] >= 1 and info["node_of_device"] >= -1
+
+
+def test_multi_slab_calls_fail_loudly_without_a_device(F):
+    """no CPU path behind the slab / group entry points either"""
+    p = F.make_params(0.02, 0.02, 0.02, 0.001, 6e-13, 1e-10, 2, 1)
+    if __import__("torch").cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    with pytest.raises(F.FdtdError) as e:
+        F.Context(p, device=0, rank=1, nranks=2)
+    assert e.value.code == -3
+    with pytest.raises(F.FdtdError) as e:
+        F.Group(p, 2, devices=[0, 0])
+    assert e.value.code == -3
